@@ -1,0 +1,224 @@
+"""Device context: the role the reference's `Net: MpcSerNet` handle plays for every `d_*` primitive
+(/root/reference/dist-primitives/src/channel/mod.rs:8-56, mpc-net/src/lib.rs:37-156) -- it names
+"where the parties are".  Here a party is one B200: `Net` wraps one `b200zk_ctx` (one process per GPU)
+and, when torch.distributed is initialised, the NCCL world that replaces the king/client star."""
+from __future__ import annotations
+
+import ctypes
+import json
+from enum import IntEnum
+
+import numpy as np
+
+from . import _native
+from ._native import B200zkError, c_vp
+
+
+class MultiplexedStreamID(IntEnum):
+    """mpc-net/src/lib.rs:29-33 -- three logical channels; here three CUDA stream slots."""
+    Zero = 0
+    One = 1
+    Two = 2
+
+
+class MpcNetError(Exception):
+    """mpc-net/src/lib.rs:15-26.  `Generic(String)` is what `?` produces from arkworks' msm
+    `Err(min_len)` at dist-primitives/src/dmsm/mod.rs:82."""
+
+    def __init__(self, kind: str, message: str):
+        super().__init__("%s(%s)" % (kind, message))
+        self.kind = kind
+        self.message = message
+
+
+def _as_u64(a, width: int) -> np.ndarray:
+    arr = np.ascontiguousarray(a, dtype=np.uint64)
+    if arr.ndim == 1 and width and arr.size % width == 0:
+        arr = arr.reshape(-1, width)
+    return arr
+
+
+def _ptr(arr: np.ndarray):
+    return ctypes.c_void_p(arr.ctypes.data)
+
+
+class Net:
+    """One GPU party.  `Net()` picks cuda:LOCAL_RANK (or cuda:0)."""
+
+    def __init__(self, device: int | None = None):
+        import os
+        self._lib = _native.lib()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        h = c_vp()
+        rc = self._lib.b200zk_ctx_create(int(device), ctypes.byref(h))
+        if rc != 0:
+            raise B200zkError(rc, "cannot create a CUDA context on device %d (no CPU fallback exists)" % device)
+        self._h = h
+        self.device = int(device)
+
+    # -- mpc-net::MpcNet surface that still makes sense -------------------------------------
+    def party_id(self) -> int:
+        try:
+            import torch.distributed as dist
+            return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        except Exception:
+            return 0
+
+    def n_parties(self) -> int:
+        try:
+            import torch.distributed as dist
+            return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        except Exception:
+            return 1
+
+    def is_king(self) -> bool:
+        return self.party_id() == 0
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b200zk_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc: int):
+        if rc != 0:
+            msg = self._lib.b200zk_last_error(self._h).decode()
+            if rc == _native.ERR_LENGTH:
+                raise MpcNetError("Generic", msg)
+            raise B200zkError(rc, msg)
+
+    def use_torch_stream(self, sid: int = 0):
+        import torch
+        self.check(self._lib.b200zk_ctx_set_stream(self._h, int(sid), c_vp(torch.cuda.current_stream().cuda_stream)))
+
+    def sync(self, sid: int = 0):
+        self.check(self._lib.b200zk_ctx_sync(self._h, int(sid)))
+
+    def profile(self, on: bool = True):
+        self.check(self._lib.b200zk_profile_enable(self._h, int(on)))
+
+    def profile_reset(self):
+        self.check(self._lib.b200zk_profile_reset(self._h))
+
+    def profile_report(self) -> dict:
+        buf = ctypes.create_string_buffer(1 << 16)
+        self.check(self._lib.b200zk_profile_json(self._h, buf, len(buf)))
+        return json.loads(buf.value.decode())
+
+    def launch_count(self) -> int:
+        return int(self._lib.b200zk_launch_count(self._h))
+
+    # -- raw calls (host numpy buffers) -----------------------------------------------------------
+    def msm(self, bases, scalars, g2: bool = False, sid: int = 0):
+        w = 16 if g2 else 8
+        b = _as_u64(bases, w)
+        s = _as_u64(scalars, 4)
+        out = np.zeros(w, dtype=np.uint64)
+        inf = ctypes.c_int(0)
+        fn = self._lib.b200zk_msm_g2 if g2 else self._lib.b200zk_msm_g1
+        self.check(fn(self._h, int(sid), _ptr(b), b.shape[0] if b.size else 0, _ptr(s), s.shape[0] if s.size else 0,
+                      _ptr(out), ctypes.byref(inf)))
+        return out, bool(inf.value)
+
+    def ntt(self, data, inverse=False, coset=False, bitrev_in=False, bitrev_out=False, pad: int = 1, sid: int = 0):
+        x = _as_u64(data, 4)
+        n = x.shape[0]
+        log_n = n.bit_length() - 1
+        if n == 0 or (1 << log_n) != n:
+            raise B200zkError(_native.ERR_DOMAIN, "length must be a power of two")
+        buf = np.zeros((n * pad, 4), dtype=np.uint64)
+        buf[:n] = x
+        self.check(self._lib.b200zk_ntt_fr(self._h, int(sid), _ptr(buf), log_n, int(inverse), int(coset), int(bitrev_in),
+                                           int(bitrev_out), int(pad)))
+        return buf
+
+    def h_circom(self, a, b, c):
+        a, b, c = (_as_u64(v, 4) for v in (a, b, c))
+        m = a.shape[0]
+        log_m = m.bit_length() - 1
+        if (1 << log_m) != m or b.shape[0] != m or c.shape[0] != m:
+            raise B200zkError(_native.ERR_DOMAIN, "a, b, c must share a power-of-two length")
+        out = np.zeros((m, 4), dtype=np.uint64)
+        self.check(self._lib.b200zk_h_circom(self._h, _ptr(a), _ptr(b), _ptr(c), log_m, _ptr(out)))
+        return out
+
+    def field_op(self, field: int, op: int, a, b):
+        a, b = _as_u64(a, 4), _as_u64(b, 4)
+        out = np.zeros_like(a)
+        self.check(self._lib.b200zk_test_field_op(self._h, field, op, _ptr(a), _ptr(b), _ptr(out), a.shape[0]))
+        return out
+
+    # -- device-resident (torch tensors, int64 view of the u64 limbs) -----------------------------
+    def _dev(self):
+        import torch
+        return torch.device("cuda", self.device)
+
+    def generate_g1(self, seed: int, n: int):
+        import torch
+        t = torch.empty((n, 8), dtype=torch.int64, device=self._dev())
+        self.check(self._lib.b200zk_g1_generate_dev(self._h, ctypes.c_uint64(seed), n, c_vp(t.data_ptr())))
+        self.sync(0)
+        return t
+
+    def generate_g2(self, seed: int, n: int):
+        import torch
+        t = torch.empty((n, 16), dtype=torch.int64, device=self._dev())
+        self.check(self._lib.b200zk_g2_generate_dev(self._h, ctypes.c_uint64(seed), n, c_vp(t.data_ptr())))
+        self.sync(0)
+        return t
+
+    def generate_fr(self, seed: int, n: int):
+        import torch
+        t = torch.empty((n, 4), dtype=torch.int64, device=self._dev())
+        self.check(self._lib.b200zk_fr_generate_dev(self._h, ctypes.c_uint64(seed), n, c_vp(t.data_ptr())))
+        self.sync(0)
+        return t
+
+    def msm_dev(self, bases, scalars, out_xyzz=None, g2: bool = False, sid: int = 0):
+        """bases/scalars: CUDA int64 tensors; returns a CUDA tensor holding the XYZZ partial."""
+        import torch
+        n = int(bases.shape[0])
+        if int(scalars.shape[0]) != n:
+            raise MpcNetError("Generic", str(min(n, int(scalars.shape[0]))))
+        if out_xyzz is None:
+            out_xyzz = torch.empty(32 if g2 else 16, dtype=torch.int64, device=bases.device)
+        fn = self._lib.b200zk_msm_g2_dev if g2 else self._lib.b200zk_msm_g1_dev
+        self.check(fn(self._h, int(sid), c_vp(bases.data_ptr()), c_vp(scalars.data_ptr()), n, c_vp(out_xyzz.data_ptr())))
+        return out_xyzz
+
+    def sum_points_dev(self, xyzz, count: int, g2: bool = False, sid: int = 0):
+        w = 16 if g2 else 8
+        out = np.zeros(w, dtype=np.uint64)
+        inf = ctypes.c_int(0)
+        fn = self._lib.b200zk_g2_sum_dev if g2 else self._lib.b200zk_g1_sum_dev
+        self.check(fn(self._h, int(sid), c_vp(xyzz.data_ptr()), int(count), _ptr(out), ctypes.byref(inf)))
+        return out, bool(inf.value)
+
+    def ntt_dev(self, x, out=None, inverse=False, coset=False, batch: int = 1, sid: int = 0):
+        import torch
+        n = int(x.shape[-2]) if x.dim() >= 2 else 0
+        log_n = n.bit_length() - 1
+        if n == 0 or (1 << log_n) != n:
+            raise B200zkError(_native.ERR_DOMAIN, "length must be a power of two")
+        if out is None:
+            out = torch.empty_like(x)
+        self.check(self._lib.b200zk_ntt_fr_dev(self._h, int(sid), c_vp(x.data_ptr()), c_vp(out.data_ptr()), log_n,
+                                               int(inverse), int(coset), int(batch)))
+        return out
+
+    def h_circom_dev(self, a, b, c, out=None):
+        import torch
+        m = int(a.shape[0])
+        log_m = m.bit_length() - 1
+        if out is None:
+            out = torch.empty_like(a)
+        self.check(self._lib.b200zk_h_circom_dev(self._h, c_vp(a.data_ptr()), c_vp(b.data_ptr()), c_vp(c.data_ptr()),
+                                                 log_m, c_vp(out.data_ptr())))
+        return out

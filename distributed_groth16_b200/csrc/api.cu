@@ -1,0 +1,368 @@
+// api.cu -- the extern "C" surface declared in include/b200zk.h.
+#include <sstream>
+
+#include "common.cuh"
+
+using namespace b200zk;
+
+static const char* kVersion = "b200zk 0.1 (sm_100a)";
+
+static bool valid_slot(int s) { return s >= 0 && s < 3; }
+
+extern "C" {
+
+const char* b200zk_version(void) { return kVersion; }
+
+int b200zk_ctx_create(int device, b200zk_ctx** out) {
+    if (!out) return B200ZK_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0 || device < 0 || device >= count) return B200ZK_ERR_CUDA;   // no CPU fallback
+    if (cudaSetDevice(device) != cudaSuccess) return B200ZK_ERR_CUDA;
+    b200zk_ctx* ctx = new b200zk_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    for (int i = 0; i < 3; ++i) {
+        if (cudaStreamCreateWithFlags(&ctx->slots[i].stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete ctx;
+            return B200ZK_ERR_CUDA;
+        }
+        ctx->slots[i].owns_stream = true;
+    }
+    *out = ctx;
+    return B200ZK_OK;
+}
+
+void b200zk_ctx_destroy(b200zk_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    ntt_free_plans(ctx);
+    for (int i = 0; i < 3; ++i) {
+        Slot& s = ctx->slots[i];
+        s.ws_msm.release(); s.ws_ntt.release(); s.io_a.release(); s.io_b.release(); s.small.release();
+        if (s.owns_stream && s.stream) cudaStreamDestroy(s.stream);
+    }
+    for (auto& e : ctx->prof_pending) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
+    delete ctx;
+}
+
+const char* b200zk_last_error(const b200zk_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+int b200zk_ctx_set_stream(b200zk_ctx* ctx, int stream, void* cuda_stream) {
+    if (!ctx || !valid_slot(stream)) return B200ZK_ERR_ARG;
+    Slot& s = ctx->slots[stream];
+    std::lock_guard<std::mutex> g(s.mu);
+    if (s.owns_stream && s.stream) { cudaStreamSynchronize(s.stream); cudaStreamDestroy(s.stream); }
+    s.stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    s.owns_stream = false;
+    return B200ZK_OK;
+}
+
+int b200zk_ctx_sync(b200zk_ctx* ctx, int stream) {
+    if (!ctx || !valid_slot(stream)) return B200ZK_ERR_ARG;
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(ctx->slots[stream].stream));
+    return B200ZK_OK;
+}
+
+int b200zk_profile_enable(b200zk_ctx* ctx, int on) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    ctx->prof_on = on != 0;
+    return B200ZK_OK;
+}
+
+static void prof_drain(b200zk_ctx* ctx) {
+    std::lock_guard<std::mutex> g(ctx->prof_mu);
+    for (auto& e : ctx->prof_pending) {
+        cudaEventSynchronize(e.stop);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e.start, e.stop) == cudaSuccess) {
+            auto& acc = ctx->prof_acc[e.name];
+            acc.first += 1;
+            acc.second += ms;
+        }
+        cudaEventDestroy(e.start);
+        cudaEventDestroy(e.stop);
+    }
+    ctx->prof_pending.clear();
+}
+
+int b200zk_profile_reset(b200zk_ctx* ctx) {
+    if (!ctx) return B200ZK_ERR_ARG;
+    prof_drain(ctx);
+    std::lock_guard<std::mutex> g(ctx->prof_mu);
+    ctx->prof_acc.clear();
+    ctx->launches = 0;
+    return B200ZK_OK;
+}
+
+int b200zk_profile_json(b200zk_ctx* ctx, char* buf, size_t buf_len) {
+    if (!ctx || !buf || buf_len == 0) return B200ZK_ERR_ARG;
+    prof_drain(ctx);
+    std::ostringstream os;
+    os << "{";
+    bool first = true;
+    {
+        std::lock_guard<std::mutex> g(ctx->prof_mu);
+        for (auto& kv : ctx->prof_acc) {
+            if (!first) os << ", ";
+            first = false;
+            os << "\"" << kv.first << "\": {\"launches\": " << kv.second.first << ", \"ms\": " << kv.second.second << "}";
+        }
+    }
+    os << "}";
+    std::string s = os.str();
+    if (s.size() + 1 > buf_len) return B200ZK_ERR_ARG;
+    memcpy(buf, s.c_str(), s.size() + 1);
+    return B200ZK_OK;
+}
+
+uint64_t b200zk_launch_count(const b200zk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"
+
+// ---- MSM ---------------------------------------------------------------------------------------
+template <int G2>
+static int msm_host(b200zk_ctx* ctx, int stream, const uint64_t* bases, size_t n_bases, const uint64_t* scalars,
+                    size_t n_scalars, uint64_t* out_affine, int* out_is_inf) {
+    if (!ctx || !valid_slot(stream) || !out_affine || !out_is_inf) return B200ZK_ERR_ARG;
+    if (n_bases != n_scalars) {
+        // arkworks: `Err(min(bases.len(), scalars.len()))`, turned into MpcNetError::Generic(min_len.to_string())
+        return set_error(ctx, B200ZK_ERR_LENGTH, std::to_string(n_bases < n_scalars ? n_bases : n_scalars));
+    }
+    const size_t n = n_bases;
+    if (n && (!bases || !scalars)) return B200ZK_ERR_ARG;
+    const size_t PB = G2 ? 128 : 64, XB = G2 ? 256 : 128;
+    Slot& sl = ctx->slots[stream];
+    std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    B2_CUDA_OK(ctx, sl.io_a.reserve(n * PB + n * 32 + 64));
+    B2_CUDA_OK(ctx, sl.small.reserve(1024));
+    char* d_bases = reinterpret_cast<char*>(sl.io_a.p);
+    char* d_scalars = d_bases + n * PB;
+    if (n) {
+        B2_CUDA_OK(ctx, cudaMemcpyAsync(d_bases, bases, n * PB, cudaMemcpyHostToDevice, sl.stream));
+        B2_CUDA_OK(ctx, cudaMemcpyAsync(d_scalars, scalars, n * 32, cudaMemcpyHostToDevice, sl.stream));
+    }
+    char* sm = reinterpret_cast<char*>(sl.small.p);
+    B2_TRY(G2 ? msm_g2_dev(ctx, sl, d_bases, d_scalars, n, sm) : msm_g1_dev(ctx, sl, d_bases, d_scalars, n, sm));
+    B2_TRY(G2 ? g2_sum_dev(ctx, sl, sm, 1, sm + XB) : g1_sum_dev(ctx, sl, sm, 1, sm + XB));
+    uint64_t host[17];
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(host, sm + XB, PB + 8, cudaMemcpyDeviceToHost, sl.stream));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(sl.stream));
+    memcpy(out_affine, host, PB);
+    *out_is_inf = (int)host[PB / 8];
+    return B200ZK_OK;
+}
+
+template <int G2>
+static int sum_host(b200zk_ctx* ctx, int stream, const void* d_xyzz, size_t count, uint64_t* out_affine, int* out_is_inf) {
+    if (!ctx || !valid_slot(stream) || !out_affine || !out_is_inf) return B200ZK_ERR_ARG;
+    const size_t PB = G2 ? 128 : 64;
+    Slot& sl = ctx->slots[stream];
+    std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, sl.small.reserve(1024));
+    char* sm = reinterpret_cast<char*>(sl.small.p);
+    B2_TRY(G2 ? g2_sum_dev(ctx, sl, d_xyzz, count, sm) : g1_sum_dev(ctx, sl, d_xyzz, count, sm));
+    uint64_t host[17];
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(host, sm, PB + 8, cudaMemcpyDeviceToHost, sl.stream));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(sl.stream));
+    memcpy(out_affine, host, PB);
+    *out_is_inf = (int)host[PB / 8];
+    return B200ZK_OK;
+}
+
+extern "C" {
+
+int b200zk_msm_g1(b200zk_ctx* ctx, int stream, const uint64_t* bases, size_t n_bases, const uint64_t* scalars,
+                  size_t n_scalars, uint64_t out_affine[8], int* out_is_inf) {
+    return msm_host<0>(ctx, stream, bases, n_bases, scalars, n_scalars, out_affine, out_is_inf);
+}
+int b200zk_msm_g2(b200zk_ctx* ctx, int stream, const uint64_t* bases, size_t n_bases, const uint64_t* scalars,
+                  size_t n_scalars, uint64_t out_affine[16], int* out_is_inf) {
+    return msm_host<1>(ctx, stream, bases, n_bases, scalars, n_scalars, out_affine, out_is_inf);
+}
+
+int b200zk_msm_g1_dev(b200zk_ctx* ctx, int stream, const void* d_bases, const void* d_scalars, size_t n, void* d_out) {
+    if (!ctx || !valid_slot(stream) || !d_out) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[stream];
+    std::lock_guard<std::mutex> g(sl.mu);
+    return msm_g1_dev(ctx, sl, d_bases, d_scalars, n, d_out);
+}
+int b200zk_msm_g2_dev(b200zk_ctx* ctx, int stream, const void* d_bases, const void* d_scalars, size_t n, void* d_out) {
+    if (!ctx || !valid_slot(stream) || !d_out) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[stream];
+    std::lock_guard<std::mutex> g(sl.mu);
+    return msm_g2_dev(ctx, sl, d_bases, d_scalars, n, d_out);
+}
+
+int b200zk_g1_sum_dev(b200zk_ctx* ctx, int stream, const void* d, size_t count, uint64_t out[8], int* inf) {
+    return sum_host<0>(ctx, stream, d, count, out, inf);
+}
+int b200zk_g2_sum_dev(b200zk_ctx* ctx, int stream, const void* d, size_t count, uint64_t out[16], int* inf) {
+    return sum_host<1>(ctx, stream, d, count, out, inf);
+}
+
+// ---- NTT ---------------------------------------------------------------------------------------
+int b200zk_ntt_fr(b200zk_ctx* ctx, int stream, uint64_t* data, unsigned log_n, int inverse, int coset, int bitrev_in,
+                  int bitrev_out, unsigned pad) {
+    if (!ctx || !valid_slot(stream) || !data) return B200ZK_ERR_ARG;
+    if (log_n > 28) return set_error(ctx, B200ZK_ERR_DOMAIN, "log_n > 28 exceeds the two-adicity of BN254 Fr");
+    if (pad == 0) pad = 1;
+    if (pad & (pad - 1)) return set_error(ctx, B200ZK_ERR_ARG, "pad must be a power of two");
+    const size_t n = (size_t)1 << log_n, n_out = n * pad;
+    unsigned log_out = log_n + ceil_log2(pad);
+    Slot& sl = ctx->slots[stream];
+    std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    B2_CUDA_OK(ctx, sl.io_a.reserve(2 * n_out * sizeof(Fr)));
+    Fr* b0 = reinterpret_cast<Fr*>(sl.io_a.p);
+    Fr* b1 = b0 + n_out;
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(b0, data, n * sizeof(Fr), cudaMemcpyHostToDevice, sl.stream));
+    Fr* cur = b0; Fr* other = b1;
+    if (bitrev_in) { B2_TRY(bitrev_dev(ctx, sl, cur, other, log_n)); std::swap(cur, other); }
+    B2_TRY(ntt_dev(ctx, sl, cur, other, log_n, inverse != 0, coset != 0, 1));
+    std::swap(cur, other);
+    if (pad > 1) B2_CUDA_OK(ctx, cudaMemsetAsync(cur + n, 0, (n_out - n) * sizeof(Fr), sl.stream));
+    if (bitrev_out) { B2_TRY(bitrev_dev(ctx, sl, cur, other, log_out)); std::swap(cur, other); }
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(data, cur, n_out * sizeof(Fr), cudaMemcpyDeviceToHost, sl.stream));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(sl.stream));
+    return B200ZK_OK;
+}
+
+int b200zk_ntt_fr_dev(b200zk_ctx* ctx, int stream, const void* d_in, void* d_out, unsigned log_n, int inverse, int coset,
+                      unsigned batch) {
+    if (!ctx || !valid_slot(stream) || !d_in || !d_out || batch == 0) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[stream];
+    std::lock_guard<std::mutex> g(sl.mu);
+    return ntt_dev(ctx, sl, reinterpret_cast<const Fr*>(d_in), reinterpret_cast<Fr*>(d_out), log_n, inverse != 0,
+                   coset != 0, batch);
+}
+
+int b200zk_ntt_fr_fourstep_cols_dev(b200zk_ctx* ctx, int stream, const void* d_in, void* d_out, unsigned log_rows,
+                                    unsigned log_cols_local, unsigned log_n, uint64_t global_col0, int inverse) {
+    if (!ctx || !valid_slot(stream)) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[stream];
+    std::lock_guard<std::mutex> g(sl.mu);
+    return fourstep_cols_dev(ctx, sl, reinterpret_cast<const Fr*>(d_in), reinterpret_cast<Fr*>(d_out), log_rows,
+                             log_cols_local, log_n, global_col0, inverse != 0);
+}
+
+// ---- h -----------------------------------------------------------------------------------------
+int b200zk_h_circom_dev(b200zk_ctx* ctx, const void* d_a, const void* d_b, const void* d_c, unsigned log_m, void* d_h) {
+    if (!ctx || !d_a || !d_b || !d_c || !d_h) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[0];
+    std::lock_guard<std::mutex> g(sl.mu);
+    return h_circom_dev(ctx, sl, (const Fr*)d_a, (const Fr*)d_b, (const Fr*)d_c, log_m, (Fr*)d_h);
+}
+
+int b200zk_h_circom(b200zk_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* c, unsigned log_m, uint64_t* h_out) {
+    if (!ctx || !a || !b || !c || !h_out) return B200ZK_ERR_ARG;
+    if (log_m + 1 > 28) return set_error(ctx, B200ZK_ERR_DOMAIN, "2m exceeds the 2^28 subgroup (PolynomialDegreeTooLarge)");
+    const size_t m = (size_t)1 << log_m;
+    Slot& sl = ctx->slots[0];
+    std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    B2_CUDA_OK(ctx, sl.io_a.reserve(4 * m * sizeof(Fr)));
+    Fr* d = reinterpret_cast<Fr*>(sl.io_a.p);
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(d, a, m * sizeof(Fr), cudaMemcpyHostToDevice, sl.stream));
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(d + m, b, m * sizeof(Fr), cudaMemcpyHostToDevice, sl.stream));
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(d + 2 * m, c, m * sizeof(Fr), cudaMemcpyHostToDevice, sl.stream));
+    B2_TRY(h_circom_dev(ctx, sl, d, d + m, d + 2 * m, log_m, d + 3 * m));
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(h_out, d + 3 * m, m * sizeof(Fr), cudaMemcpyDeviceToHost, sl.stream));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(sl.stream));
+    return B200ZK_OK;
+}
+
+// ---- proving key + prove -----------------------------------------------------------------------
+static int upload(b200zk_ctx* ctx, void** dst, const void* src, size_t bytes) {
+    *dst = nullptr;
+    if (bytes == 0) bytes = 16;
+    B2_CUDA_OK(ctx, cudaMalloc(dst, bytes + 16));
+    if (src) B2_CUDA_OK(ctx, cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    return B200ZK_OK;
+}
+
+int b200zk_pk_upload(b200zk_ctx* ctx, const uint64_t* a_query, const uint64_t* b_g1_query, const uint64_t* b_g2_query,
+                     const uint64_t* l_query, const uint64_t* h_query, size_t n_vars, size_t n_inputs, size_t m,
+                     const uint64_t* vk_points, b200zk_pk** out) {
+    if (!ctx || !out || !a_query || !b_g1_query || !b_g2_query || !h_query || !vk_points) return B200ZK_ERR_ARG;
+    if (n_vars == 0 || n_inputs == 0 || n_inputs > n_vars) return set_error(ctx, B200ZK_ERR_ARG, "need 1 <= n_inputs <= n_vars");
+    if (m == 0 || (m & (m - 1))) return set_error(ctx, B200ZK_ERR_DOMAIN, "h_query length must be a power of two");
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    b200zk_pk* pk = new b200zk_pk();
+    pk->n_vars = n_vars; pk->n_inputs = n_inputs; pk->m = m;
+    int rc = upload(ctx, &pk->a_query, a_query, n_vars * 64);
+    if (!rc) rc = upload(ctx, &pk->b_g1_query, b_g1_query, n_vars * 64);
+    if (!rc) rc = upload(ctx, &pk->b_g2_query, b_g2_query, n_vars * 128);
+    if (!rc) rc = upload(ctx, &pk->l_query, l_query, (n_vars - n_inputs) * 64);
+    if (!rc) rc = upload(ctx, &pk->h_query, h_query, m * 64);
+    if (!rc) rc = upload(ctx, &pk->vk, vk_points, 56 * 8);
+    if (rc) { b200zk_pk_free(ctx, pk); return rc; }
+    *out = pk;
+    return B200ZK_OK;
+}
+
+void b200zk_pk_free(b200zk_ctx* ctx, b200zk_pk* pk) {
+    if (!pk) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    void* ptrs[6] = {pk->a_query, pk->b_g1_query, pk->b_g2_query, pk->l_query, pk->h_query, pk->vk};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    delete pk;
+}
+
+int b200zk_groth16_prove(b200zk_ctx* ctx, const b200zk_pk* pk, const uint64_t* z, const uint64_t* a, const uint64_t* b,
+                         const uint64_t* c, const uint64_t r[4], const uint64_t s[4], int mirror_bg1, uint8_t proof_out[128]) {
+    if (!ctx || !pk || !z || !a || !b || !c || !r || !s || !proof_out) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[0];
+    std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    const size_t m = pk->m, nv = pk->n_vars;
+    B2_CUDA_OK(ctx, sl.io_a.reserve((nv + 3 * m) * sizeof(Fr)));
+    Fr* d_z = reinterpret_cast<Fr*>(sl.io_a.p);
+    Fr* d_abc = d_z + nv;
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(d_z, z, nv * sizeof(Fr), cudaMemcpyHostToDevice, sl.stream));
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(d_abc, a, m * sizeof(Fr), cudaMemcpyHostToDevice, sl.stream));
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(d_abc + m, b, m * sizeof(Fr), cudaMemcpyHostToDevice, sl.stream));
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(d_abc + 2 * m, c, m * sizeof(Fr), cudaMemcpyHostToDevice, sl.stream));
+    return prove_dev(ctx, pk, d_z, d_abc, d_abc + m, d_abc + 2 * m, r, s, mirror_bg1, proof_out);
+}
+
+// ---- generators / self-test --------------------------------------------------------------------
+int b200zk_g1_generate_dev(b200zk_ctx* ctx, uint64_t seed, size_t n, void* d_out) {
+    if (!ctx || (n && !d_out)) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[0];
+    std::lock_guard<std::mutex> g(sl.mu);
+    return generate_points_dev(ctx, sl, 0, seed, n, d_out);
+}
+int b200zk_g2_generate_dev(b200zk_ctx* ctx, uint64_t seed, size_t n, void* d_out) {
+    if (!ctx || (n && !d_out)) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[0];
+    std::lock_guard<std::mutex> g(sl.mu);
+    return generate_points_dev(ctx, sl, 1, seed, n, d_out);
+}
+int b200zk_fr_generate_dev(b200zk_ctx* ctx, uint64_t seed, size_t n, void* d_out) {
+    if (!ctx || (n && !d_out)) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[0];
+    std::lock_guard<std::mutex> g(sl.mu);
+    return generate_fr_dev(ctx, sl, seed, n, d_out);
+}
+
+int b200zk_test_field_op(b200zk_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+    if (!ctx || !a || !b || !out) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[0];
+    std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    B2_CUDA_OK(ctx, sl.io_a.reserve(3 * n * 32 + 64));
+    char* d = reinterpret_cast<char*>(sl.io_a.p);
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(d, a, n * 32, cudaMemcpyHostToDevice, sl.stream));
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(d + n * 32, b, n * 32, cudaMemcpyHostToDevice, sl.stream));
+    B2_TRY(field_op_dev(ctx, sl, field, op, d, d + n * 32, d + 2 * n * 32, n));
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(out, d + 2 * n * 32, n * 32, cudaMemcpyDeviceToHost, sl.stream));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(sl.stream));
+    return B200ZK_OK;
+}
+
+}  // extern "C"

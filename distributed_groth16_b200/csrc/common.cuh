@@ -1,0 +1,165 @@
+// common.cuh -- context, error handling, workspace and per-kernel event profiling shared by the
+// translation units of libb200zk.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200zk.h"
+#include "ec.cuh"
+
+namespace b200zk {
+
+struct ProfEntry {
+    const char* name;
+    cudaEvent_t start, stop;
+};
+
+struct NttPlan;   // ntt.cu
+
+// grow-only device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Slot {                 // one per MultiplexedStreamID
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    std::mutex mu;            // same-slot calls are serialised
+    DevBuf ws_msm;            // MSM workspace
+    DevBuf ws_ntt;            // NTT ping-pong
+    DevBuf io_a, io_b;        // staging for host-buffer entry points
+    DevBuf small;             // results
+};
+
+}  // namespace b200zk
+
+struct b200zk_ctx {
+    int device = 0;
+    int sm_count = 148;
+    b200zk::Slot slots[3];
+    std::string last_error;
+    std::mutex err_mu;
+    // profiling
+    bool prof_on = false;
+    std::mutex prof_mu;
+    std::vector<b200zk::ProfEntry> prof_pending;
+    std::map<std::string, std::pair<uint64_t, double>> prof_acc;   // name -> (launches, ms)
+    uint64_t launches = 0;
+    // NTT plans keyed by (log_n << 1 | inverse)
+    std::mutex plan_mu;
+    std::map<uint32_t, b200zk::NttPlan*> plans;
+};
+
+struct b200zk_pk {
+    size_t n_vars = 0, n_inputs = 0, m = 0;
+    void *a_query = nullptr, *b_g1_query = nullptr, *b_g2_query = nullptr, *l_query = nullptr, *h_query = nullptr;
+    void* vk = nullptr;       // device copy of the 56 vk limbs
+};
+
+namespace b200zk {
+
+inline int set_error(b200zk_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) {
+        std::lock_guard<std::mutex> g(ctx->err_mu);
+        ctx->last_error = msg;
+    }
+    return code;
+}
+
+#define B2_CUDA_OK(ctx, expr)                                                                         \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            char _b[512];                                                                             \
+            snprintf(_b, sizeof(_b), "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__, \
+                     __LINE__, #expr);                                                                \
+            return set_error((ctx), _e == cudaErrorMemoryAllocation ? B200ZK_ERR_OOM : B200ZK_ERR_CUDA, _b); \
+        }                                                                                             \
+    } while (0)
+
+#define B2_TRY(expr)                 \
+    do {                             \
+        int _rc = (expr);            \
+        if (_rc != B200ZK_OK) return _rc; \
+    } while (0)
+
+// RAII kernel-launch bracket: counts launches and, when profiling is on, records an event pair.
+struct LaunchScope {
+    b200zk_ctx* ctx;
+    cudaStream_t st;
+    ProfEntry e;
+    bool active;
+    LaunchScope(b200zk_ctx* c, cudaStream_t s, const char* name) : ctx(c), st(s), active(false) {
+        ctx->launches++;
+        if (ctx->prof_on) {
+            e.name = name;
+            cudaEventCreate(&e.start);
+            cudaEventCreate(&e.stop);
+            cudaEventRecord(e.start, st);
+            active = true;
+        }
+    }
+    ~LaunchScope() {
+        if (active) {
+            cudaEventRecord(e.stop, st);
+            std::lock_guard<std::mutex> g(ctx->prof_mu);
+            ctx->prof_pending.push_back(e);
+        }
+    }
+};
+
+inline int check_launch(b200zk_ctx* ctx, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        char b[256];
+        snprintf(b, sizeof(b), "kernel launch failed (%s): %s", what, cudaGetErrorString(e));
+        return set_error(ctx, B200ZK_ERR_CUDA, b);
+    }
+    return B200ZK_OK;
+}
+
+static inline unsigned ceil_log2(size_t n) {
+    unsigned l = 0;
+    while (((size_t)1 << l) < n) ++l;
+    return l;
+}
+
+// ---- entry points implemented across translation units -------------------------------------
+// ntt.cu
+int ntt_dev(b200zk_ctx* ctx, Slot& sl, const Fr* d_in, Fr* d_out, unsigned log_n, bool inverse, bool coset,
+            unsigned batch);
+int h_circom_dev(b200zk_ctx* ctx, Slot& sl, const Fr* d_a, const Fr* d_b, const Fr* d_c, unsigned log_m, Fr* d_h);
+int bitrev_dev(b200zk_ctx* ctx, Slot& sl, const Fr* d_in, Fr* d_out, unsigned log_n);
+int fourstep_cols_dev(b200zk_ctx* ctx, Slot& sl, const Fr* d_in, Fr* d_out, unsigned log_rows,
+                      unsigned log_cols_local, unsigned log_n, uint64_t global_col0, bool inverse);
+void ntt_free_plans(b200zk_ctx* ctx);
+// msm.cu
+int msm_g1_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n, void* d_out_xyzz);
+int msm_g2_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n, void* d_out_xyzz);
+int g1_sum_dev(b200zk_ctx* ctx, Slot& sl, const void* d_xyzz, size_t count, void* d_out_affine);
+int g2_sum_dev(b200zk_ctx* ctx, Slot& sl, const void* d_xyzz, size_t count, void* d_out_affine);
+int generate_points_dev(b200zk_ctx* ctx, Slot& sl, int g2, uint64_t seed, size_t n, void* d_out);
+int generate_fr_dev(b200zk_ctx* ctx, Slot& sl, uint64_t seed, size_t n, void* d_out);
+int field_op_dev(b200zk_ctx* ctx, Slot& sl, int field, int op, const void* d_a, const void* d_b, void* d_out, size_t n);
+// prove.cu
+int prove_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, const Fr* d_a, const Fr* d_b, const Fr* d_c,
+              const uint64_t r[4], const uint64_t s[4], int mirror_bg1, uint8_t proof_out[128]);
+
+}  // namespace b200zk

@@ -1,0 +1,264 @@
+// fp.cuh -- 256-bit Montgomery prime-field arithmetic for sm_100a (BN254 Fq and Fr).
+//
+// Replaces arkworks' `Fp256<MontBackend<..,4>>` (un-vendored dependency of the reference; used at
+// every hot-path site, e.g. /root/reference/dist-primitives/src/dfft/mod.rs:128-131 butterflies and
+// inside `G::msm` at dist-primitives/src/dmsm/mod.rs:82).
+//
+// Representation: 8 x 32-bit little-endian limbs, Montgomery form with R = 2^256, value always
+// canonical (< p) between operations.  The memory image of one element (32 bytes) is identical to
+// arkworks' 4 x u64 `BigInt` limbs, which is what crosses the C ABI (include/b200zk.h).
+//
+// The multiplier is a row-interleaved Montgomery product built from PTX carry-chain multiply-adds
+// (mad.lo.cc / madc.hi.cc); two accumulators hold the products of the even- and odd-indexed limbs
+// of `a` so that every 64-bit partial product lands on an aligned (lo,hi) register pair and ptxas
+// can emit IMAD.WIDE with carry.  There are no tensor cores anywhere: the arithmetic is wide-integer.
+//
+// Every primitive has a plain-C emulation behind `#ifndef __CUDA_ARCH__` so the exact same limb
+// schedule is unit-tested on the CPU (tests/host/fp_host_test.cpp) -- this is a test seam, not a CPU
+// fallback: no product entry point runs the host branch.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define B2_HD __host__ __device__ __forceinline__
+#define B2_HD_NI __host__ __device__ __noinline__
+#else
+#define B2_HD inline __attribute__((always_inline))
+#define B2_HD_NI inline
+#endif
+
+namespace b200zk {
+
+// ---------------------------------------------------------------------------------------------
+// carry-chain primitives
+// ---------------------------------------------------------------------------------------------
+namespace cc {
+#ifdef __CUDA_ARCH__
+#define B2_ASM asm volatile
+B2_HD uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; B2_ASM("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B2_HD uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; B2_ASM("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B2_HD uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; B2_ASM("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B2_HD uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; B2_ASM("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B2_HD uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; B2_ASM("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B2_HD uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; B2_ASM("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B2_HD uint32_t mul_lo(uint32_t a, uint32_t b) { uint32_t r; B2_ASM("mul.lo.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B2_HD uint32_t mul_hi(uint32_t a, uint32_t b) { uint32_t r; B2_ASM("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+B2_HD uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; B2_ASM("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+B2_HD uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; B2_ASM("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+B2_HD uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; B2_ASM("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+B2_HD uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; B2_ASM("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+B2_HD uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; B2_ASM("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+B2_HD uint32_t madc_lo(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; B2_ASM("madc.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+#undef B2_ASM
+#else
+// host emulation of the PTX condition-code register (test seam only)
+static thread_local uint32_t CF = 0;
+B2_HD uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b; CF = (uint32_t)(t >> 32); return (uint32_t)t; }
+B2_HD uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + CF; CF = (uint32_t)(t >> 32); return (uint32_t)t; }
+B2_HD uint32_t addc(uint32_t a, uint32_t b) { return a + b + CF; }
+B2_HD uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b; CF = (uint32_t)(t >> 32) & 1; return (uint32_t)t; }
+B2_HD uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - CF; CF = (uint32_t)(t >> 32) & 1; return (uint32_t)t; }
+B2_HD uint32_t subc(uint32_t a, uint32_t b) { return a - b - CF; }
+B2_HD uint32_t mul_lo(uint32_t a, uint32_t b) { return a * b; }
+B2_HD uint32_t mul_hi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+B2_HD uint32_t mad_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)(uint32_t)(a * b) + c; CF = (uint32_t)(t >> 32); return (uint32_t)t; }
+B2_HD uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (uint64_t)(uint32_t)(a * b) + c + CF; CF = (uint32_t)(t >> 32); return (uint32_t)t; }
+B2_HD uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (((uint64_t)a * b) >> 32) + c; CF = (uint32_t)(t >> 32); return (uint32_t)t; }
+B2_HD uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint64_t t = (((uint64_t)a * b) >> 32) + c + CF; CF = (uint32_t)(t >> 32); return (uint32_t)t; }
+B2_HD uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)((((uint64_t)a * b) >> 32) + c + CF); }
+B2_HD uint32_t madc_lo(uint32_t a, uint32_t b, uint32_t c) { return a * b + c + CF; }
+#endif
+}  // namespace cc
+
+// ---------------------------------------------------------------------------------------------
+// field parameters (BN254).  MOD = p, INV = -p^{-1} mod 2^32, R1 = 2^256 mod p, R2 = 2^512 mod p.
+// Values are generated by tools/gen_constants.py from oracle/bn254.py and re-checked by
+// tests/test_constants.py; they are compile-time so ptxas can fold them into immediates.
+// ---------------------------------------------------------------------------------------------
+#include "bn254_constants.inc"
+
+template <class P>
+struct Fp {
+    uint32_t l[8];
+
+    B2_HD static Fp zero() { Fp r; for (int i = 0; i < 8; ++i) r.l[i] = 0; return r; }
+    B2_HD static Fp one() { Fp r; for (int i = 0; i < 8; ++i) r.l[i] = P::r1(i); return r; }
+    B2_HD static Fp r2() { Fp r; for (int i = 0; i < 8; ++i) r.l[i] = P::r2(i); return r; }
+    B2_HD bool is_zero() const {
+        uint32_t o = 0;
+        for (int i = 0; i < 8; ++i) o |= l[i];
+        return o == 0;
+    }
+    B2_HD bool operator==(const Fp& b) const {
+        uint32_t o = 0;
+        for (int i = 0; i < 8; ++i) o |= l[i] ^ b.l[i];
+        return o == 0;
+    }
+    B2_HD bool operator!=(const Fp& b) const { return !(*this == b); }
+
+    // r = t - p if t >= p else t   (t < 2p)
+    B2_HD static void final_sub(Fp& r, const uint32_t t[8]) {
+        uint32_t d[8];
+        d[0] = cc::sub_cc(t[0], P::mod(0));
+#pragma unroll
+        for (int i = 1; i < 8; ++i) d[i] = cc::subc_cc(t[i], P::mod(i));
+        uint32_t borrow = cc::subc(0, 0);       // 0xffffffff when t < p
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.l[i] = borrow ? t[i] : d[i];
+    }
+
+    B2_HD static Fp add(const Fp& a, const Fp& b) {
+        uint32_t t[8];
+        t[0] = cc::add_cc(a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < 7; ++i) t[i] = cc::addc_cc(a.l[i], b.l[i]);
+        t[7] = cc::addc(a.l[7], b.l[7]);        // a+b < 2p < 2^255: no carry out
+        Fp r; final_sub(r, t); return r;
+    }
+    B2_HD static Fp sub(const Fp& a, const Fp& b) {
+        uint32_t t[8];
+        t[0] = cc::sub_cc(a.l[0], b.l[0]);
+#pragma unroll
+        for (int i = 1; i < 8; ++i) t[i] = cc::subc_cc(a.l[i], b.l[i]);
+        uint32_t borrow = cc::subc(0, 0);       // all ones when a < b
+        Fp r;
+        r.l[0] = cc::add_cc(t[0], P::mod(0) & borrow);
+#pragma unroll
+        for (int i = 1; i < 7; ++i) r.l[i] = cc::addc_cc(t[i], P::mod(i) & borrow);
+        r.l[7] = cc::addc(t[7], P::mod(7) & borrow);
+        return r;
+    }
+    B2_HD static Fp neg(const Fp& a) { return sub(zero(), a); }
+    B2_HD static Fp dbl(const Fp& a) { return add(a, a); }
+
+    // ---- Montgomery product --------------------------------------------------------------
+    // acc[j], acc[j+1] = a[j]*bi for even j (no carries)
+    B2_HD static void mul_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            acc[j] = cc::mul_lo(a[j], bi);
+            acc[j + 1] = cc::mul_hi(a[j], bi);
+        }
+    }
+    // acc += sum_{even j} a[j]*bi * 2^(32 j); carry-out left in CC
+    B2_HD static void cmad_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+        acc[0] = cc::mad_lo_cc(a[0], bi, acc[0]);
+        acc[1] = cc::madc_hi_cc(a[0], bi, acc[1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            acc[j] = cc::madc_lo_cc(a[j], bi, acc[j]);
+            acc[j + 1] = cc::madc_hi_cc(a[j], bi, acc[j + 1]);
+        }
+    }
+    // acc += sum_{even j} p[j+OFF]*mi * 2^(32 j); carry-out left in CC
+    template <int OFF>
+    B2_HD static void cmad_mod(uint32_t* acc, uint32_t mi) {
+        acc[0] = cc::mad_lo_cc(P::mod(OFF), mi, acc[0]);
+        acc[1] = cc::madc_hi_cc(P::mod(OFF), mi, acc[1]);
+#pragma unroll
+        for (int j = 2; j < 8; j += 2) {
+            acc[j] = cc::madc_lo_cc(P::mod(j + OFF), mi, acc[j]);
+            acc[j + 1] = cc::madc_hi_cc(P::mod(j + OFF), mi, acc[j + 1]);
+        }
+    }
+    // acc = (acc >> 64) + sum_{even j} a[j]*bi * 2^(32 j) + CC  (top product < 2^62: no carry out)
+    B2_HD static void madc_n_rshift(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+#pragma unroll
+        for (int j = 0; j < 6; j += 2) {
+            acc[j] = cc::madc_lo_cc(a[j], bi, acc[j + 2]);
+            acc[j + 1] = cc::madc_hi_cc(a[j], bi, acc[j + 3]);
+        }
+        acc[6] = cc::madc_lo_cc(a[6], bi, 0);
+        acc[7] = cc::madc_hi(a[6], bi, 0);
+    }
+    // one row: (ev + 2^32 od) <- (ev + 2^32 od + a*bi + m*p) / 2^32, roles of ev/od swap for the next row
+    B2_HD static void mad_row(uint32_t* ev, uint32_t* od, const uint32_t* a, uint32_t bi, bool first) {
+        if (first) {
+            mul_n(od, a + 1, bi);
+            mul_n(ev, a, bi);
+        } else {
+            ev[0] = cc::add_cc(ev[0], od[1]);
+            madc_n_rshift(od, a + 1, bi);
+            cmad_n(ev, a, bi);
+            od[7] = cc::addc(od[7], 0);
+        }
+        uint32_t mi = ev[0] * P::INV;
+        cmad_mod<1>(od, mi);
+        cmad_mod<0>(ev, mi);
+        od[7] = cc::addc(od[7], 0);
+    }
+    B2_HD static Fp mul(const Fp& a, const Fp& b) {
+        uint32_t ev[8], od[8];
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+            mad_row(ev, od, a.l, b.l[i], i == 0);
+            mad_row(od, ev, a.l, b.l[i + 1], false);
+        }
+        ev[0] = cc::add_cc(ev[0], od[1]);
+#pragma unroll
+        for (int i = 1; i < 7; ++i) ev[i] = cc::addc_cc(ev[i], od[i + 1]);
+        ev[7] = cc::addc(ev[7], 0);
+        Fp r; final_sub(r, ev); return r;
+    }
+    B2_HD static Fp sqr(const Fp& a) { return mul(a, a); }
+    // out-of-line copy for the cold / very large kernels (G2, reductions): keeps code size and
+    // compile time bounded; the G1 bucket loop uses the inlined `mul`.
+    B2_HD_NI static Fp mul_ni(const Fp& a, const Fp& b) { return mul(a, b); }
+
+    B2_HD static Fp to_mont(const Fp& a) { return mul(a, r2()); }
+    B2_HD static Fp from_mont(const Fp& a) {
+        Fp o = zero(); o.l[0] = 1;
+        return mul(a, o);
+    }
+    // a^(p-2) (Fermat); only used for the handful of affine normalisations per call
+    B2_HD_NI static Fp inv(const Fp& a) {
+        Fp res = one();
+        for (int i = 255; i >= 0; --i) {
+            res = mul_ni(res, res);
+            uint32_t w = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) if ((i >> 5) == k) w = P::mod_m2(k);
+            if ((w >> (i & 31)) & 1) res = mul_ni(res, a);
+        }
+        return res;
+    }
+    B2_HD static Fp from_u32(uint32_t v) { Fp o = zero(); o.l[0] = v; return to_mont(o); }
+};
+
+typedef Fp<FqParams> Fq;
+typedef Fp<FrParams> Fr;
+
+// ---------------------------------------------------------------------------------------------
+// Fq2 = Fq[u]/(u^2 + 1)   (arkworks Fq2Config for BN254: NONRESIDUE = -1)
+// ---------------------------------------------------------------------------------------------
+struct Fq2 {
+    Fq c0, c1;
+    B2_HD static Fq2 zero() { Fq2 r; r.c0 = Fq::zero(); r.c1 = Fq::zero(); return r; }
+    B2_HD static Fq2 one() { Fq2 r; r.c0 = Fq::one(); r.c1 = Fq::zero(); return r; }
+    B2_HD bool is_zero() const { return c0.is_zero() && c1.is_zero(); }
+    B2_HD bool operator==(const Fq2& b) const { return c0 == b.c0 && c1 == b.c1; }
+    B2_HD bool operator!=(const Fq2& b) const { return !(*this == b); }
+    B2_HD static Fq2 add(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = Fq::add(a.c0, b.c0); r.c1 = Fq::add(a.c1, b.c1); return r; }
+    B2_HD static Fq2 sub(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = Fq::sub(a.c0, b.c0); r.c1 = Fq::sub(a.c1, b.c1); return r; }
+    B2_HD static Fq2 neg(const Fq2& a) { Fq2 r; r.c0 = Fq::neg(a.c0); r.c1 = Fq::neg(a.c1); return r; }
+    B2_HD static Fq2 dbl(const Fq2& a) { return add(a, a); }
+    B2_HD static Fq2 mul(const Fq2& a, const Fq2& b) {
+        Fq v0 = Fq::mul_ni(a.c0, b.c0), v1 = Fq::mul_ni(a.c1, b.c1);
+        Fq s = Fq::mul_ni(Fq::add(a.c0, a.c1), Fq::add(b.c0, b.c1));
+        Fq2 r;
+        r.c0 = Fq::sub(v0, v1);
+        r.c1 = Fq::sub(Fq::sub(s, v0), v1);
+        return r;
+    }
+    B2_HD static Fq2 sqr(const Fq2& a) {
+        Fq t = Fq::mul_ni(Fq::add(a.c0, a.c1), Fq::sub(a.c0, a.c1));
+        Fq u = Fq::mul_ni(a.c0, a.c1);
+        Fq2 r; r.c0 = t; r.c1 = Fq::dbl(u); return r;
+    }
+    B2_HD static Fq2 inv(const Fq2& a) {
+        Fq n = Fq::inv(Fq::add(Fq::mul_ni(a.c0, a.c0), Fq::mul_ni(a.c1, a.c1)));
+        Fq2 r; r.c0 = Fq::mul_ni(a.c0, n); r.c1 = Fq::neg(Fq::mul_ni(a.c1, n)); return r;
+    }
+};
+
+}  // namespace b200zk

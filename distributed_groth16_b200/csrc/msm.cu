@@ -1,0 +1,472 @@
+// msm.cu -- Pippenger bucket MSM over BN254 G1 / G2 for sm_100a.
+//
+// Replaces `G::msm(bases, scalars)` -- THE hot line of the reference
+// (/root/reference/dist-primitives/src/dmsm/mod.rs:82, reached from groth16/src/prove.rs:41,80,119,121,123)
+// which is arkworks' CPU `VariableBaseMSM::msm_bigint_wnaf`.  The result is the same group element
+// sum_i scalars[i] * bases[i]; only its canonical affine form ever leaves the library.
+//
+// Pipeline (all on one stream, no host round trips):
+//   1 digits     scalar Montgomery -> canonical, signed c-bit windows; per (window, |digit|) histogram
+//                with atomics that also hand every entry its rank inside the bucket
+//   2 scan       exclusive prefix sum of the W * 2^(c-1) bucket sizes
+//   3 scatter    entries[offset[bucket] + rank] = point index | sign  (counting sort, no comparison sort)
+//   4 accumulate one thread per bucket: gather affine points (the 2^20 x 64 B base array sits in the
+//                126 MB L2), mixed XYZZ additions
+//   5 reduce     per window sum_b b * bucket_b as segment running sums + small scalar multiples,
+//                tree-combined per window in shared memory
+//   6 combine    Horner over windows (c doublings each)
+#include "common.cuh"
+
+namespace b200zk {
+
+static const uint32_t KEY_NONE = 0xFFFFFFFFu;
+
+template <class T>
+__device__ __forceinline__ T ld16(const T* p) {
+    static_assert(sizeof(T) % 16 == 0, "16-byte multiple");
+    T r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); ++i) d[i] = s[i];
+    return r;
+}
+template <class T>
+__device__ __forceinline__ void st16(T* p, const T& v) {
+    static_assert(sizeof(T) % 16 == 0, "16-byte multiple");
+    const uint4* s = reinterpret_cast<const uint4*>(&v);
+    uint4* d = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); ++i) d[i] = s[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1. digits + histogram
+// ---------------------------------------------------------------------------------------------
+__global__ void k_msm_digits(const Fr* scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t* keys, uint32_t* ranks,
+                             uint32_t* counts) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr s = Fr::from_mont(ld16(scalars + i));
+    uint32_t k[9];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) k[j] = s.l[j];
+    k[8] = 0;
+    const uint32_t B = 1u << (c - 1);
+    const uint32_t mask = (1u << c) - 1;
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < W; ++w) {
+        uint32_t off = w * c, limb = off >> 5, sh = off & 31;
+        uint64_t v = limb < 8 ? ((uint64_t)k[limb] | ((uint64_t)k[limb + 1] << 32)) : 0;
+        uint32_t d = ((uint32_t)(v >> sh) & mask) + carry;
+        uint32_t key = KEY_NONE, rank = 0;
+        carry = 0;
+        uint32_t neg = 0;
+        if (d > B) { d = (1u << c) - d; neg = 1; carry = 1; }
+        if (d != 0) {
+            uint32_t g = w * B + (d - 1);
+            rank = atomicAdd(counts + g, 1u);
+            key = g | (neg << 31);
+        }
+        keys[(size_t)w * n + i] = key;
+        ranks[(size_t)w * n + i] = rank;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2. exclusive scan (uint32), three small kernels
+// ---------------------------------------------------------------------------------------------
+static const uint32_t SCAN_THREADS = 512, SCAN_ITEMS = 4, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total, uint32_t* warp_sums) {
+    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= (uint32_t)o) x += y;
+    }
+    if (lane == 31) warp_sums[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t nw = blockDim.x >> 5;
+        uint32_t s = lane < nw ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= (uint32_t)o) s += y;
+        }
+        if (lane < nw) warp_sums[lane] = s;
+    }
+    __syncthreads();
+    uint32_t base = wid ? warp_sums[wid - 1] : 0;
+    *total = warp_sums[(blockDim.x >> 5) - 1];
+    return base + x - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_local(const uint32_t* in, uint32_t* out, uint32_t* sums, uint32_t n) {
+    __shared__ uint32_t warp_sums[32];
+    uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t v[SCAN_ITEMS], t = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < SCAN_ITEMS; ++j) { v[j] = base + j < n ? in[base + j] : 0; t += v[j]; }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(t, &total, warp_sums);
+#pragma unroll
+    for (uint32_t j = 0; j < SCAN_ITEMS; ++j) { if (base + j < n) out[base + j] = ex; ex += v[j]; }
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(uint32_t* sums, uint32_t n) {
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += SCAN_THREADS) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t v = i < n ? sums[i] : 0, total;
+        uint32_t ex = block_exclusive_scan(v, &total, warp_sums);
+        uint32_t carry = carry_s;
+        if (i < n) sums[i] = ex + carry;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + total;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t* out, const uint32_t* sums, uint32_t n) {
+    uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    uint32_t add = sums[blockIdx.x];
+#pragma unroll
+    for (uint32_t j = 0; j < SCAN_ITEMS; ++j) if (base + j < n) out[base + j] += add;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3. scatter
+// ---------------------------------------------------------------------------------------------
+__global__ void k_msm_scatter(const uint32_t* keys, const uint32_t* ranks, const uint32_t* offsets, uint32_t n,
+                              size_t total, uint32_t* entries) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    uint32_t key = keys[t];
+    if (key == KEY_NONE) return;
+    uint32_t i = (uint32_t)(t % n);
+    uint32_t g = key & 0x7FFFFFFFu;
+    entries[offsets[g] + ranks[t]] = i | (key & 0x80000000u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 4. bucket accumulation
+// ---------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_accumulate(const affine_t<F>* bases, const uint32_t* entries, const uint32_t* offsets,
+                                 uint32_t nbuckets, xyzz_t<F>* buckets) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nbuckets) return;
+    uint32_t lo = offsets[g], hi = offsets[g + 1];
+    xyzz_t<F> acc = xyzz_t<F>::identity();
+    for (uint32_t k = lo; k < hi; ++k) {
+        uint32_t e = entries[k];
+        affine_t<F> p = ld16(bases + (e & 0x7FFFFFFFu));
+        xyzz_t<F>::madd(acc, p, (e >> 31) != 0);
+    }
+    st16(buckets + g, acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 5. window reduction: S_w = sum_{k<B} (k+1) * bucket[w][k]
+// ---------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_reduce_segments(const xyzz_t<F>* buckets, uint32_t W, uint32_t B, uint32_t seg_len,
+                                      xyzz_t<F>* partials) {
+    uint32_t nseg = B / seg_len;
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= W * nseg) return;
+    uint32_t w = t / nseg, seg = t % nseg;
+    uint32_t lo = seg * seg_len;
+    const xyzz_t<F>* bw = buckets + (size_t)w * B;
+    xyzz_t<F> run = xyzz_t<F>::identity(), acc = xyzz_t<F>::identity();
+    for (uint32_t k = lo + seg_len; k-- > lo;) {
+        run = xyzz_t<F>::add(run, ld16(bw + k));
+        acc = xyzz_t<F>::add(acc, run);
+    }
+    if (lo) {   // + lo * run
+        xyzz_t<F> m = xyzz_t<F>::identity();
+        for (int bit = 31 - __clz(lo); bit >= 0; --bit) {
+            m = xyzz_t<F>::dbl(m);
+            if ((lo >> bit) & 1) m = xyzz_t<F>::add(m, run);
+        }
+        acc = xyzz_t<F>::add(acc, m);
+    }
+    st16(partials + t, acc);
+}
+
+// one block per window: sum nseg partials
+template <class F, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_msm_window_sum(const xyzz_t<F>* partials, uint32_t nseg, xyzz_t<F>* wsum) {
+    __shared__ xyzz_t<F> sh[THREADS];
+    const xyzz_t<F>* p = partials + (size_t)blockIdx.x * nseg;
+    xyzz_t<F> acc = xyzz_t<F>::identity();
+    for (uint32_t i = threadIdx.x; i < nseg; i += THREADS) acc = xyzz_t<F>::add(acc, ld16(p + i));
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            xyzz_t<F> a = sh[threadIdx.x], b = sh[threadIdx.x + s];
+            sh[threadIdx.x] = xyzz_t<F>::add(a, b);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st16(wsum + blockIdx.x, sh[0]);
+}
+
+// 6. Horner over windows
+template <class F>
+__global__ void k_msm_combine(const xyzz_t<F>* wsum, uint32_t W, uint32_t c, xyzz_t<F>* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    xyzz_t<F> total = ld16(wsum + (W - 1));
+    for (int w = (int)W - 2; w >= 0; --w) {
+        for (uint32_t k = 0; k < c; ++k) total = xyzz_t<F>::dbl(total);
+        total = xyzz_t<F>::add(total, ld16(wsum + w));
+    }
+    st16(out, total);
+}
+
+// sum `count` XYZZ points, normalise; out = affine followed by one u64 infinity flag
+template <class F>
+__global__ void k_sum_to_affine(const xyzz_t<F>* pts, uint32_t count, affine_t<F>* out, uint64_t* flag) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    xyzz_t<F> acc = xyzz_t<F>::identity();
+    for (uint32_t i = 0; i < count; ++i) acc = xyzz_t<F>::add(acc, ld16(pts + i));
+    affine_t<F> a = xyzz_t<F>::to_affine(acc);
+    st16(out, a);
+    *flag = acc.is_inf() ? 1 : 0;
+}
+
+template <class F>
+__global__ void k_set_identity(xyzz_t<F>* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) st16(out, xyzz_t<F>::identity());
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static unsigned choose_window(size_t n) {
+    unsigned lg = ceil_log2(n < 2 ? 2 : n);
+    int c = (int)lg - 4;
+    if (c < 5) c = 5;
+    if (c > 20) c = 20;
+    const char* env = getenv("B200ZK_MSM_WINDOW");
+    if (env) { int v = atoi(env); if (v >= 2 && v <= 24) c = v; }
+    return (unsigned)c;
+}
+
+static int exclusive_scan(b200zk_ctx* ctx, cudaStream_t st, const uint32_t* in, uint32_t* out, uint32_t* sums, uint32_t n) {
+    uint32_t nblk = (n + SCAN_TILE - 1) / SCAN_TILE;
+    {
+        LaunchScope ls(ctx, st, "msm_scan");
+        k_scan_local<<<nblk, SCAN_THREADS, 0, st>>>(in, out, sums, n);
+    }
+    {
+        LaunchScope ls(ctx, st, "msm_scan");
+        k_scan_sums<<<1, SCAN_THREADS, 0, st>>>(sums, nblk);
+    }
+    {
+        LaunchScope ls(ctx, st, "msm_scan");
+        k_scan_add<<<nblk, SCAN_THREADS, 0, st>>>(out, sums, n);
+    }
+    return check_launch(ctx, "scan");
+}
+
+template <class F>
+static int msm_dev_impl(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n, void* d_out,
+                        const char* acc_name) {
+    cudaStream_t st = sl.stream;
+    xyzz_t<F>* out = reinterpret_cast<xyzz_t<F>*>(d_out);
+    if (n == 0) {
+        LaunchScope ls(ctx, st, "msm_small");
+        k_set_identity<F><<<1, 32, 0, st>>>(out);
+        return check_launch(ctx, "k_set_identity");
+    }
+    if (n >= (1ull << 31)) return set_error(ctx, B200ZK_ERR_ARG, "MSM length must be < 2^31");
+    const unsigned c = choose_window(n);
+    const unsigned W = (255 + c - 1) / c;
+    const uint32_t B = 1u << (c - 1);
+    const uint32_t nb = W * B;
+    uint32_t seg_len = B < 16 ? B : 16;
+    const uint32_t nseg = B / seg_len;
+    const size_t total = (size_t)W * n;
+
+    // workspace carve-up (256-byte aligned)
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    size_t o_keys = 0;
+    size_t o_ranks = o_keys + al(total * 4);
+    size_t o_entries = o_ranks + al(total * 4);
+    size_t o_counts = o_entries + al(total * 4);
+    size_t o_offsets = o_counts + al(((size_t)nb + 1) * 4);
+    size_t o_sums = o_offsets + al(((size_t)nb + 1) * 4);
+    size_t o_buckets = o_sums + al(((size_t)nb / SCAN_TILE + 2) * 4);
+    size_t o_partials = o_buckets + al((size_t)nb * sizeof(xyzz_t<F>));
+    size_t o_wsum = o_partials + al((size_t)W * nseg * sizeof(xyzz_t<F>));
+    size_t ws_bytes = o_wsum + al((size_t)W * sizeof(xyzz_t<F>));
+    B2_CUDA_OK(ctx, sl.ws_msm.reserve(ws_bytes));
+    char* ws = reinterpret_cast<char*>(sl.ws_msm.p);
+    uint32_t* keys = reinterpret_cast<uint32_t*>(ws + o_keys);
+    uint32_t* ranks = reinterpret_cast<uint32_t*>(ws + o_ranks);
+    uint32_t* entries = reinterpret_cast<uint32_t*>(ws + o_entries);
+    uint32_t* counts = reinterpret_cast<uint32_t*>(ws + o_counts);
+    uint32_t* offsets = reinterpret_cast<uint32_t*>(ws + o_offsets);
+    uint32_t* sums = reinterpret_cast<uint32_t*>(ws + o_sums);
+    xyzz_t<F>* buckets = reinterpret_cast<xyzz_t<F>*>(ws + o_buckets);
+    xyzz_t<F>* partials = reinterpret_cast<xyzz_t<F>*>(ws + o_partials);
+    xyzz_t<F>* wsum = reinterpret_cast<xyzz_t<F>*>(ws + o_wsum);
+
+    B2_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, ((size_t)nb + 1) * 4, st));
+    {
+        LaunchScope ls(ctx, st, "msm_digits");
+        k_msm_digits<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const Fr*>(d_scalars), (uint32_t)n, c, W,
+                                                                    keys, ranks, counts);
+    }
+    B2_TRY(check_launch(ctx, "k_msm_digits"));
+    B2_TRY(exclusive_scan(ctx, st, counts, offsets, sums, nb + 1));
+    {
+        LaunchScope ls(ctx, st, "msm_scatter");
+        k_msm_scatter<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(keys, ranks, offsets, (uint32_t)n, total, entries);
+    }
+    B2_TRY(check_launch(ctx, "k_msm_scatter"));
+    {
+        LaunchScope ls(ctx, st, acc_name);
+        k_msm_accumulate<F><<<(nb + 127) / 128, 128, 0, st>>>(reinterpret_cast<const affine_t<F>*>(d_bases), entries, offsets,
+                                                               nb, buckets);
+    }
+    B2_TRY(check_launch(ctx, "k_msm_accumulate"));
+    {
+        LaunchScope ls(ctx, st, "msm_reduce");
+        k_msm_reduce_segments<F><<<(W * nseg + 127) / 128, 128, 0, st>>>(buckets, W, B, seg_len, partials);
+    }
+    B2_TRY(check_launch(ctx, "k_msm_reduce_segments"));
+    {
+        LaunchScope ls(ctx, st, "msm_reduce");
+        constexpr int T = sizeof(F) > 32 ? 128 : 256;
+        k_msm_window_sum<F, T><<<W, T, 0, st>>>(partials, nseg, wsum);
+    }
+    B2_TRY(check_launch(ctx, "k_msm_window_sum"));
+    {
+        LaunchScope ls(ctx, st, "msm_combine");
+        k_msm_combine<F><<<1, 32, 0, st>>>(wsum, W, c, out);
+    }
+    return check_launch(ctx, "k_msm_combine");
+}
+
+int msm_g1_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n, void* d_out) {
+    return msm_dev_impl<Fq>(ctx, sl, d_bases, d_scalars, n, d_out, "msm_accumulate_g1");
+}
+int msm_g2_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n, void* d_out) {
+    return msm_dev_impl<Fq2>(ctx, sl, d_bases, d_scalars, n, d_out, "msm_accumulate_g2");
+}
+
+template <class F>
+static int sum_impl(b200zk_ctx* ctx, Slot& sl, const void* d_xyzz, size_t count, void* d_out_affine) {
+    affine_t<F>* out = reinterpret_cast<affine_t<F>*>(d_out_affine);
+    {
+        LaunchScope ls(ctx, sl.stream, "point_normalise");
+        k_sum_to_affine<F><<<1, 32, 0, sl.stream>>>(reinterpret_cast<const xyzz_t<F>*>(d_xyzz), (uint32_t)count, out,
+                                                     reinterpret_cast<uint64_t*>(out + 1));
+    }
+    return check_launch(ctx, "k_sum_to_affine");
+}
+int g1_sum_dev(b200zk_ctx* ctx, Slot& sl, const void* d, size_t count, void* d_out) { return sum_impl<Fq>(ctx, sl, d, count, d_out); }
+int g2_sum_dev(b200zk_ctx* ctx, Slot& sl, const void* d, size_t count, void* d_out) { return sum_impl<Fq2>(ctx, sl, d, count, d_out); }
+
+// ---------------------------------------------------------------------------------------------
+// deterministic dummy inputs + element-wise self-test
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+
+template <class F> __device__ affine_t<F> curve_generator();
+template <> __device__ affine_t<Fq> curve_generator<Fq>() {
+    affine_t<Fq> g;
+    for (int i = 0; i < 8; ++i) { g.x.l[i] = CurveConst::g1_gen_x(i); g.y.l[i] = CurveConst::g1_gen_y(i); }
+    return g;
+}
+template <> __device__ affine_t<Fq2> curve_generator<Fq2>() {
+    affine_t<Fq2> g;
+    for (int i = 0; i < 8; ++i) {
+        g.x.c0.l[i] = CurveConst::g2_gen_x0(i); g.x.c1.l[i] = CurveConst::g2_gen_x1(i);
+        g.y.c0.l[i] = CurveConst::g2_gen_y0(i); g.y.c1.l[i] = CurveConst::g2_gen_y1(i);
+    }
+    return g;
+}
+
+// P_i = k_i * G, k_i = splitmix64(seed + i) | 1
+template <class F>
+__global__ void __launch_bounds__(128) k_generate_points(uint64_t seed, size_t n, affine_t<F>* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t k = splitmix64(seed + i) | 1ULL;
+    affine_t<F> g = curve_generator<F>();
+    xyzz_t<F> acc = xyzz_t<F>::identity();
+    for (int bit = 63; bit >= 0; --bit) {
+        acc = xyzz_t<F>::dbl(acc);
+        if ((k >> bit) & 1) xyzz_t<F>::madd(acc, g, false);
+    }
+    st16(out + i, xyzz_t<F>::to_affine(acc));
+}
+
+__global__ void k_generate_fr(uint64_t seed, size_t n, Fr* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t v[4];
+    for (int k = 0; k < 4; ++k) v[k] = splitmix64(seed * 0x100000001B3ULL + 4 * (uint64_t)i + k);
+    v[3] &= 0x3FFFFFFFFFFFFFFFULL;
+    uint32_t t[8];
+    for (int k = 0; k < 4; ++k) { t[2 * k] = (uint32_t)v[k]; t[2 * k + 1] = (uint32_t)(v[k] >> 32); }
+    Fr r;
+    Fr::final_sub(r, t);      // v < 2^254 < 2r
+    st16(out + i, r);
+}
+
+template <class F>
+__global__ void k_field_op(int op, const F* a, const F* b, F* out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F x = ld16(a + i), y = ld16(b + i), r;
+    if (op == 0) r = F::mul(x, y);
+    else if (op == 1) r = F::add(x, y);
+    else r = F::sub(x, y);
+    st16(out + i, r);
+}
+
+int generate_points_dev(b200zk_ctx* ctx, Slot& sl, int g2, uint64_t seed, size_t n, void* d_out) {
+    if (n == 0) return B200ZK_OK;
+    {
+        LaunchScope ls(ctx, sl.stream, "generate_points");
+        unsigned grid = (unsigned)((n + 127) / 128);
+        if (g2) k_generate_points<Fq2><<<grid, 128, 0, sl.stream>>>(seed, n, reinterpret_cast<affine_t<Fq2>*>(d_out));
+        else k_generate_points<Fq><<<grid, 128, 0, sl.stream>>>(seed, n, reinterpret_cast<affine_t<Fq>*>(d_out));
+    }
+    return check_launch(ctx, "k_generate_points");
+}
+int generate_fr_dev(b200zk_ctx* ctx, Slot& sl, uint64_t seed, size_t n, void* d_out) {
+    if (n == 0) return B200ZK_OK;
+    {
+        LaunchScope ls(ctx, sl.stream, "generate_fr");
+        k_generate_fr<<<(unsigned)((n + 255) / 256), 256, 0, sl.stream>>>(seed, n, reinterpret_cast<Fr*>(d_out));
+    }
+    return check_launch(ctx, "k_generate_fr");
+}
+int field_op_dev(b200zk_ctx* ctx, Slot& sl, int field, int op, const void* d_a, const void* d_b, void* d_out, size_t n) {
+    if (n == 0) return B200ZK_OK;
+    {
+        LaunchScope ls(ctx, sl.stream, "field_op");
+        unsigned grid = (unsigned)((n + 255) / 256);
+        if (field == 0) k_field_op<Fq><<<grid, 256, 0, sl.stream>>>(op, (const Fq*)d_a, (const Fq*)d_b, (Fq*)d_out, n);
+        else k_field_op<Fr><<<grid, 256, 0, sl.stream>>>(op, (const Fr*)d_a, (const Fr*)d_b, (Fr*)d_out, n);
+    }
+    return check_launch(ctx, "k_field_op");
+}
+
+}  // namespace b200zk

@@ -1,0 +1,388 @@
+// ntt.cu -- radix-2 Cooley-Tukey NTT / iNTT over BN254 Fr as Stockham passes through shared memory.
+//
+// Replaces `d_fft` / `d_ifft` (/root/reference/dist-primitives/src/dfft/mod.rs:17-95: fft1 butterflies
+// :122-135, king-side fft2 :161-175, size_inv scaling :78) whose contract, once the protocol's own
+// bit-reverse/stride packing and `rotate_right(1)` are accounted for, is the natural-order
+// `Radix2EvaluationDomain::{fft,ifft}` (asserted at dfft/mod.rs:304,373,384,458), and the
+// h-polynomial pipeline `ext_wit::h` (groth16/src/ext_wit.rs:16-101) ==
+// `CircomReduction::witness_map_from_matrices` (ark-circom/src/circom/qap.rs:64-89).
+//
+// Decomposition N = R_1 R_2 .. R_p (R_s = 2^k, k <= MAX_LOG_R).  Pass s, with L = R_1..R_{s-1} and
+// M = N / (L R_s), views its input as T_s[j][n_s][n''] (j < L, n_s < R_s, n'' < M), performs the R_s-point
+// DIT NTT along n_s in shared memory (root w_N^(N/R_s)), multiplies output k_s by w_N^(L n'' k_s) and
+// writes T_{s+1}[j + L k_s][n''].  After the last pass the array is X in natural order, so no separate
+// bit-reversal pass over HBM is needed (the reference's `fft_in_place_rearrange`, dfft/mod.rs:258-271,
+// is folded into the shared-memory placement).  A block owns G consecutive columns, so every global
+// access is a run of G x 32 B.
+#include "common.cuh"
+
+namespace b200zk {
+
+static const unsigned MAX_LOG_R = 8;
+static const unsigned LOG_G = 2;
+
+struct PowTab {
+    const Fr* lo;
+    const Fr* hi;
+    uint32_t lo_bits;
+};
+
+struct NttPlan {
+    unsigned log_n = 0;
+    bool inverse = false;
+    unsigned npass = 0;
+    unsigned logR[8];
+    Fr* twR[8];          // per pass: w_R^i, i < R/2
+    Fr* consts = nullptr;  // [0] w_N (direction applied) [1] n^-1 [2] coset generator (g or g^-1) [3] w_2N (forward)
+    PowTab tw;           // powers of consts[0]
+    PowTab coset;        // powers of consts[2]   (lazy)
+    PowTab shift;        // powers of consts[3]   (lazy; used by h)
+    std::vector<void*> allocs;
+};
+
+__device__ __forceinline__ Fr ld_fr(const Fr* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    Fr r;
+    r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+    r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void st_fr(Fr* p, const Fr& v) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+    q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+}
+
+__device__ __forceinline__ Fr powtab_get(const PowTab& t, uint64_t e) {
+    Fr lo = ld_fr(t.lo + (e & ((1ull << t.lo_bits) - 1)));
+    uint64_t hi_i = e >> t.lo_bits;
+    if (hi_i == 0) return lo;
+    return Fr::mul(lo, ld_fr(t.hi + hi_i));
+}
+
+__device__ Fr fr_pow_u64(Fr base, uint64_t e) {
+    Fr res = Fr::one();
+    while (e) {
+        if (e & 1) res = Fr::mul(res, base);
+        base = Fr::sqr(base);
+        e >>= 1;
+    }
+    return res;
+}
+
+// consts[0] = w_N (or its inverse), [1] = N^-1, [2] = g (or g^-1), [3] = w_2N (forward; one if log_n = 28)
+__global__ void k_plan_consts(unsigned log_n, int inverse, Fr* consts) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    Fr w, g;
+    for (int i = 0; i < 8; ++i) {
+        w.l[i] = inverse ? FrParams::root28_inv(i) : FrParams::root28(i);
+        g.l[i] = inverse ? FrParams::gen_inv(i) : FrParams::gen(i);
+    }
+    for (unsigned k = log_n; k < 28; ++k) w = Fr::sqr(w);
+    consts[0] = w;
+    Fr two = Fr::add(Fr::one(), Fr::one());
+    Fr n = Fr::one();
+    for (unsigned k = 0; k < log_n; ++k) n = Fr::mul(n, two);
+    consts[1] = Fr::inv(n);
+    consts[2] = g;
+    Fr w2;
+    for (int i = 0; i < 8; ++i) w2.l[i] = FrParams::root28(i);
+    if (log_n + 1 <= 28) {
+        for (unsigned k = log_n + 1; k < 28; ++k) w2 = Fr::sqr(w2);
+    } else {
+        w2 = Fr::one();
+    }
+    consts[3] = w2;
+}
+
+// out[i] = base^(i << shift)
+__global__ void k_build_pow(const Fr* base_ptr, Fr* out, uint32_t count, uint32_t shift) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    st_fr(out + i, fr_pow_u64(*base_ptr, (uint64_t)i << shift));
+}
+
+struct PassParams {
+    const Fr* in;
+    Fr* out;
+    uint32_t log_n, logL, logR, logM, logG;
+    const Fr* twR;
+    PowTab tw;
+    PowTab pre;
+    PowTab post;
+    const Fr* post_const;
+    int apply_tw, apply_pre, apply_post, apply_post_const;
+    size_t batch_stride;
+};
+
+__global__ void __launch_bounds__(512) k_ntt_pass(PassParams p) {
+    extern __shared__ uint4 smem[];
+    const uint32_t R = 1u << p.logR, G = 1u << p.logG;
+    const uint32_t RG = R << p.logG;
+    uint4* s_lo = smem;                 // [G][R]
+    uint4* s_hi = smem + RG;
+    uint4* s_tw = smem + 2 * RG;        // [R/2][2]
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    const Fr* in = p.in + (size_t)blockIdx.y * p.batch_stride;
+    Fr* out = p.out + (size_t)blockIdx.y * p.batch_stride;
+    const uint64_t q0 = (uint64_t)blockIdx.x << p.logG;
+    const uint64_t Mmask = (1ull << p.logM) - 1;
+
+    for (uint32_t i = tid; i < R / 2; i += nt) {
+        const uint4* t = reinterpret_cast<const uint4*>(p.twR + i);
+        s_tw[2 * i] = t[0];
+        s_tw[2 * i + 1] = t[1];
+    }
+    for (uint32_t idx = tid; idx < RG; idx += nt) {
+        uint32_t c = idx & (G - 1), ns = idx >> p.logG;
+        uint64_t q = q0 + c, j = q >> p.logM, n2 = q & Mmask;
+        uint64_t addr = (j << (p.logR + p.logM)) + ((uint64_t)ns << p.logM) + n2;
+        Fr v = ld_fr(in + addr);
+        if (p.apply_pre) v = Fr::mul(v, powtab_get(p.pre, addr));
+        uint32_t slot = p.logR ? (__brev(ns) >> (32 - p.logR)) : 0;
+        uint32_t e = c * R + slot;
+        s_lo[e] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+        s_hi[e] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+    }
+    __syncthreads();
+
+    const uint32_t nbf = RG >> 1;
+    for (uint32_t s = 1; s <= p.logR; ++s) {
+        const uint32_t half = 1u << (s - 1);
+        for (uint32_t b = tid; b < nbf; b += nt) {
+            uint32_t c = b >> (p.logR - 1), bb = b & (R / 2 - 1);
+            uint32_t jj = bb & (half - 1);
+            uint32_t i0 = c * R + (((bb >> (s - 1)) << s) | jj), i1 = i0 + half;
+            uint4 ul = s_lo[i0], uh = s_hi[i0], vl = s_lo[i1], vh = s_hi[i1];
+            Fr u, v;
+            u.l[0] = ul.x; u.l[1] = ul.y; u.l[2] = ul.z; u.l[3] = ul.w; u.l[4] = uh.x; u.l[5] = uh.y; u.l[6] = uh.z; u.l[7] = uh.w;
+            v.l[0] = vl.x; v.l[1] = vl.y; v.l[2] = vl.z; v.l[3] = vl.w; v.l[4] = vh.x; v.l[5] = vh.y; v.l[6] = vh.z; v.l[7] = vh.w;
+            if (s > 1) {
+                uint32_t ti = jj << (p.logR - s);
+                uint4 tl = s_tw[2 * ti], th = s_tw[2 * ti + 1];
+                Fr t;
+                t.l[0] = tl.x; t.l[1] = tl.y; t.l[2] = tl.z; t.l[3] = tl.w; t.l[4] = th.x; t.l[5] = th.y; t.l[6] = th.z; t.l[7] = th.w;
+                v = Fr::mul(v, t);
+            }
+            Fr x = Fr::add(u, v), y = Fr::sub(u, v);
+            s_lo[i0] = make_uint4(x.l[0], x.l[1], x.l[2], x.l[3]);
+            s_hi[i0] = make_uint4(x.l[4], x.l[5], x.l[6], x.l[7]);
+            s_lo[i1] = make_uint4(y.l[0], y.l[1], y.l[2], y.l[3]);
+            s_hi[i1] = make_uint4(y.l[4], y.l[5], y.l[6], y.l[7]);
+        }
+        __syncthreads();
+    }
+
+    for (uint32_t idx = tid; idx < RG; idx += nt) {
+        uint32_t c = idx & (G - 1), ks = idx >> p.logG;
+        uint64_t q = q0 + c, j = q >> p.logM, n2 = q & Mmask;
+        uint32_t e = c * R + ks;
+        uint4 a = s_lo[e], bq = s_hi[e];
+        Fr v;
+        v.l[0] = a.x; v.l[1] = a.y; v.l[2] = a.z; v.l[3] = a.w; v.l[4] = bq.x; v.l[5] = bq.y; v.l[6] = bq.z; v.l[7] = bq.w;
+        if (p.apply_tw) {
+            uint64_t ex = (n2 * ks) << p.logL;
+            if (ex) v = Fr::mul(v, powtab_get(p.tw, ex));
+        }
+        uint64_t oaddr = ((j + ((uint64_t)ks << p.logL)) << p.logM) + n2;
+        if (p.apply_post) v = Fr::mul(v, powtab_get(p.post, oaddr));
+        if (p.apply_post_const) v = Fr::mul(v, ld_fr(p.post_const));
+        st_fr(out + oaddr, v);
+    }
+}
+
+__global__ void k_bitrev(const Fr* in, Fr* out, unsigned log_n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ((size_t)1 << log_n)) return;
+    size_t j = log_n ? (size_t)(__brevll((unsigned long long)i) >> (64 - log_n)) : 0;
+    st_fr(out + j, ld_fr(in + i));
+}
+
+// h[i] = a[i]*b[i] - c[i]
+__global__ void k_h_pointwise(const Fr* a, const Fr* b, const Fr* c, Fr* h, size_t m) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    st_fr(h + i, Fr::sub(Fr::mul(ld_fr(a + i), ld_fr(b + i)), ld_fr(c + i)));
+}
+
+static int build_powtab(b200zk_ctx* ctx, cudaStream_t st, NttPlan* pl, const Fr* base, unsigned log_range, PowTab* out) {
+    unsigned lo_bits = (log_range + 1) / 2, hi_bits = log_range - lo_bits;
+    Fr *lo = nullptr, *hi = nullptr;
+    B2_CUDA_OK(ctx, cudaMalloc(&lo, sizeof(Fr) << lo_bits));
+    pl->allocs.push_back(lo);
+    B2_CUDA_OK(ctx, cudaMalloc(&hi, sizeof(Fr) << hi_bits));
+    pl->allocs.push_back(hi);
+    {
+        LaunchScope ls(ctx, st, "ntt_build_tables");
+        uint32_t cnt = 1u << lo_bits;
+        k_build_pow<<<(cnt + 127) / 128, 128, 0, st>>>(base, lo, cnt, 0);
+    }
+    {
+        LaunchScope ls(ctx, st, "ntt_build_tables");
+        uint32_t cnt = 1u << hi_bits;
+        k_build_pow<<<(cnt + 127) / 128, 128, 0, st>>>(base, hi, cnt, lo_bits);
+    }
+    out->lo = lo; out->hi = hi; out->lo_bits = lo_bits;
+    return check_launch(ctx, "k_build_pow");
+}
+
+static int get_plan(b200zk_ctx* ctx, cudaStream_t st, unsigned log_n, bool inverse, NttPlan** out) {
+    std::lock_guard<std::mutex> g(ctx->plan_mu);
+    uint32_t key = (log_n << 1) | (inverse ? 1u : 0u);
+    auto it = ctx->plans.find(key);
+    if (it != ctx->plans.end()) { *out = it->second; return B200ZK_OK; }
+    NttPlan* pl = new NttPlan();
+    pl->log_n = log_n; pl->inverse = inverse;
+    pl->coset.lo = nullptr; pl->shift.lo = nullptr;
+    pl->npass = log_n == 0 ? 0 : (log_n + MAX_LOG_R - 1) / MAX_LOG_R;
+    for (unsigned i = 0; i < pl->npass; ++i) {
+        pl->logR[i] = log_n / pl->npass + (i < log_n % pl->npass ? 1 : 0);
+    }
+    B2_CUDA_OK(ctx, cudaMalloc(&pl->consts, 4 * sizeof(Fr)));
+    pl->allocs.push_back(pl->consts);
+    {
+        LaunchScope ls(ctx, st, "ntt_build_tables");
+        k_plan_consts<<<1, 1, 0, st>>>(log_n, inverse ? 1 : 0, pl->consts);
+    }
+    B2_TRY(check_launch(ctx, "k_plan_consts"));
+    for (unsigned i = 0; i < pl->npass; ++i) {
+        uint32_t cnt = 1u << (pl->logR[i] - 1);
+        B2_CUDA_OK(ctx, cudaMalloc(&pl->twR[i], sizeof(Fr) * cnt));
+        pl->allocs.push_back(pl->twR[i]);
+        LaunchScope ls(ctx, st, "ntt_build_tables");
+        k_build_pow<<<(cnt + 127) / 128, 128, 0, st>>>(pl->consts, pl->twR[i], cnt, log_n - pl->logR[i]);
+    }
+    B2_TRY(check_launch(ctx, "k_build_pow(twR)"));
+    B2_TRY(build_powtab(ctx, st, pl, pl->consts, log_n, &pl->tw));
+    // tables are built on `st`; other slots may use the plan later, so finish construction here
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    ctx->plans[key] = pl;
+    *out = pl;
+    return B200ZK_OK;
+}
+
+static int plan_lazy_tab(b200zk_ctx* ctx, cudaStream_t st, NttPlan* pl, int which, PowTab** out) {
+    std::lock_guard<std::mutex> g(ctx->plan_mu);
+    PowTab* t = which == 2 ? &pl->coset : &pl->shift;
+    if (!t->lo) {
+        B2_TRY(build_powtab(ctx, st, pl, pl->consts + which, pl->log_n, t));
+        B2_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    }
+    *out = t;
+    return B200ZK_OK;
+}
+
+void ntt_free_plans(b200zk_ctx* ctx) {
+    for (auto& kv : ctx->plans) {
+        for (void* p : kv.second->allocs) cudaFree(p);
+        delete kv.second;
+    }
+    ctx->plans.clear();
+}
+
+// Runs all passes.  pre / post may be null.  post_const: device pointer or null.
+static int ntt_run(b200zk_ctx* ctx, Slot& sl, NttPlan* pl, const Fr* d_in, Fr* d_out, unsigned batch,
+                   const PowTab* pre, const PowTab* post, const Fr* post_const) {
+    cudaStream_t st = sl.stream;
+    const size_t N = (size_t)1 << pl->log_n;
+    if (pl->npass == 0) {   // N == 1: X[0] = x[0] (all scale factors are 1)
+        if (d_in != d_out) B2_CUDA_OK(ctx, cudaMemcpyAsync(d_out, d_in, sizeof(Fr) * batch, cudaMemcpyDeviceToDevice, st));
+        return B200ZK_OK;
+    }
+    const size_t bytes = sizeof(Fr) * N * batch;
+    B2_CUDA_OK(ctx, sl.ws_ntt.reserve(2 * bytes));
+    Fr* scratch[2] = {reinterpret_cast<Fr*>(sl.ws_ntt.p), reinterpret_cast<Fr*>(sl.ws_ntt.p) + N * batch};
+    const Fr* cur = d_in;
+    unsigned logL = 0;
+    for (unsigned i = 0; i < pl->npass; ++i) {
+        bool last = (i + 1 == pl->npass);
+        Fr* dst = last ? d_out : scratch[(i + 1) & 1];
+        bool bounce = last && (cur == d_out);     // only when npass == 1 and in-place
+        if (bounce) dst = scratch[0];
+        PassParams p;
+        memset(&p, 0, sizeof(p));
+        p.in = cur; p.out = dst;
+        p.log_n = pl->log_n; p.logL = logL; p.logR = pl->logR[i];
+        p.logM = pl->log_n - logL - pl->logR[i];
+        unsigned log_cols = pl->log_n - pl->logR[i];
+        p.logG = log_cols < LOG_G ? log_cols : LOG_G;
+        p.twR = pl->twR[i];
+        p.tw = pl->tw;
+        p.apply_tw = last ? 0 : 1;
+        if (i == 0 && pre) { p.pre = *pre; p.apply_pre = 1; }
+        if (last && post) { p.post = *post; p.apply_post = 1; }
+        if (last && post_const) { p.post_const = post_const; p.apply_post_const = 1; }
+        p.batch_stride = N;
+        uint32_t RG = 1u << (p.logR + p.logG);
+        uint32_t threads = RG / 2 < 32 ? 32 : RG / 2;
+        size_t smem = (size_t)(2 * RG + (1u << p.logR)) * sizeof(uint4);
+        dim3 grid((unsigned)(((size_t)1 << log_cols) >> p.logG), batch);
+        {
+            LaunchScope ls(ctx, st, "ntt_pass");
+            k_ntt_pass<<<grid, threads, smem, st>>>(p);
+        }
+        B2_TRY(check_launch(ctx, "k_ntt_pass"));
+        if (bounce) B2_CUDA_OK(ctx, cudaMemcpyAsync(d_out, dst, bytes, cudaMemcpyDeviceToDevice, st));
+        cur = dst;
+        logL += pl->logR[i];
+    }
+    return B200ZK_OK;
+}
+
+int ntt_dev(b200zk_ctx* ctx, Slot& sl, const Fr* d_in, Fr* d_out, unsigned log_n, bool inverse, bool coset,
+            unsigned batch) {
+    if (log_n > 28) return set_error(ctx, B200ZK_ERR_DOMAIN, "log_n > 28 exceeds the two-adicity of BN254 Fr");
+    NttPlan* pl;
+    B2_TRY(get_plan(ctx, sl.stream, log_n, inverse, &pl));
+    PowTab* ct = nullptr;
+    if (coset && log_n > 0) B2_TRY(plan_lazy_tab(ctx, sl.stream, pl, 2, &ct));
+    if (!inverse) return ntt_run(ctx, sl, pl, d_in, d_out, batch, ct, nullptr, nullptr);
+    return ntt_run(ctx, sl, pl, d_in, d_out, batch, nullptr, ct, log_n > 0 ? pl->consts + 1 : nullptr);
+}
+
+int bitrev_dev(b200zk_ctx* ctx, Slot& sl, const Fr* d_in, Fr* d_out, unsigned log_n) {
+    size_t n = (size_t)1 << log_n;
+    {
+        LaunchScope ls(ctx, sl.stream, "bitrev");
+        k_bitrev<<<(unsigned)((n + 255) / 256), 256, 0, sl.stream>>>(d_in, d_out, log_n);
+    }
+    return check_launch(ctx, "k_bitrev");
+}
+
+// h = (NTT(shift(iNTT a)) * NTT(shift(iNTT b))) - NTT(shift(iNTT c)),  shift: coeff j *= w_2m^j
+// d_a, d_b, d_c may be separate buffers; they are staged into one [3][m] batch.
+int h_circom_dev(b200zk_ctx* ctx, Slot& sl, const Fr* d_a, const Fr* d_b, const Fr* d_c, unsigned log_m, Fr* d_h) {
+    if (log_m + 1 > 28) return set_error(ctx, B200ZK_ERR_DOMAIN, "2m exceeds the 2^28 subgroup (PolynomialDegreeTooLarge)");
+    cudaStream_t st = sl.stream;
+    const size_t m = (size_t)1 << log_m;
+    B2_CUDA_OK(ctx, sl.io_b.reserve(2 * 3 * m * sizeof(Fr)));
+    Fr* buf0 = reinterpret_cast<Fr*>(sl.io_b.p);
+    Fr* buf1 = buf0 + 3 * m;
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(buf0, d_a, m * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(buf0 + m, d_b, m * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(buf0 + 2 * m, d_c, m * sizeof(Fr), cudaMemcpyDeviceToDevice, st));
+    NttPlan *inv, *fwd;
+    B2_TRY(get_plan(ctx, st, log_m, true, &inv));
+    B2_TRY(get_plan(ctx, st, log_m, false, &fwd));
+    if (log_m == 0) {
+        // m = 1: iNTT and NTT are the identity and the shift multiplies coefficient 0 by 1
+        buf1 = buf0;
+    } else {
+        PowTab* shift;
+        B2_TRY(plan_lazy_tab(ctx, st, inv, 3, &shift));
+        B2_TRY(ntt_run(ctx, sl, inv, buf0, buf1, 3, nullptr, shift, inv->consts + 1));
+        B2_TRY(ntt_run(ctx, sl, fwd, buf1, buf1, 3, nullptr, nullptr, nullptr));
+    }
+    {
+        LaunchScope ls(ctx, st, "h_pointwise");
+        k_h_pointwise<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(buf1, buf1 + m, buf1 + 2 * m, d_h, m);
+    }
+    return check_launch(ctx, "k_h_pointwise");
+}
+
+int fourstep_cols_dev(b200zk_ctx* ctx, Slot&, const Fr*, Fr*, unsigned, unsigned, unsigned, uint64_t, bool) {
+    return set_error(ctx, B200ZK_ERR_ARG, "four-step column transform: not built yet");
+}
+
+}  // namespace b200zk

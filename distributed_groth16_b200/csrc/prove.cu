@@ -1,0 +1,147 @@
+// prove.cu -- Groth16 proof assembly on the device.
+//
+// Replaces `prove::{A,B,C}::compute` (/root/reference/groth16/src/prove.rs:21-46,62-85,106-136) plus the
+// final assembly of groth16/examples/sha256.rs:208-212,240-244 (== mpc-api/src/main.rs:600-616) and the
+// `Proof::serialize_with_mode(Compress::Yes)` of zk-cli/src/main.rs:130-136.  With the PSS layer gone
+// (single box, no secret sharing) the formulas are the single-node ones of the zkHubHQ ark-groth16 fork
+// (SURVEY 3.2):
+//   A  = alpha_g1 + a_query[0] + r*delta_g1 + MSM(a_query[1..], z[1..])
+//   B  = beta_g2  + b_g2_query[0] + s*delta_g2 + MSM_G2(b_g2_query[1..], z[1..])
+//   B1 = beta_g1  + b_g1_query[0] + s*delta_g1 + MSM(b_g1_query[1..], z[1..])      (only enters C times r)
+//   C  = MSM(l_query, z[n_inputs..]) + MSM(h_query, h) + s*A + r*B1 - r*s*delta_g1
+#include "common.cuh"
+
+namespace b200zk {
+
+template <class T>
+__device__ __forceinline__ T ldp(const void* p) {
+    T r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(T) / 16); ++i) d[i] = s[i];
+    return r;
+}
+
+__device__ bool fq_is_neg(const Fq& y) {       // arkworks: y > -y  (canonical integers)
+    Fq a = Fq::from_mont(y), b = Fq::from_mont(Fq::neg(y));
+    for (int i = 7; i >= 0; --i) {
+        if (a.l[i] > b.l[i]) return true;
+        if (a.l[i] < b.l[i]) return false;
+    }
+    return false;
+}
+
+__device__ void compress_g1(const xyzz_t<Fq>& p, uint8_t* out) {
+    for (int i = 0; i < 32; ++i) out[i] = 0;
+    if (p.is_inf()) { out[31] = 0x40; return; }
+    affine_t<Fq> a = xyzz_t<Fq>::to_affine(p);
+    Fq x = Fq::from_mont(a.x);
+    for (int i = 0; i < 32; ++i) out[i] = (uint8_t)(x.l[i >> 2] >> (8 * (i & 3)));
+    if (fq_is_neg(a.y)) out[31] |= 0x80;
+}
+
+__device__ void compress_g2(const xyzz_t<Fq2>& p, uint8_t* out) {
+    for (int i = 0; i < 64; ++i) out[i] = 0;
+    if (p.is_inf()) { out[63] = 0x40; return; }
+    affine_t<Fq2> a = xyzz_t<Fq2>::to_affine(p);
+    Fq x0 = Fq::from_mont(a.x.c0), x1 = Fq::from_mont(a.x.c1);
+    for (int i = 0; i < 32; ++i) {
+        out[i] = (uint8_t)(x0.l[i >> 2] >> (8 * (i & 3)));
+        out[32 + i] = (uint8_t)(x1.l[i >> 2] >> (8 * (i & 3)));
+    }
+    // Fq2 ordering: c1 first, then c0
+    bool neg = a.y.c1.is_zero() ? fq_is_neg(a.y.c0) : fq_is_neg(a.y.c1);
+    if (neg) out[63] |= 0x80;
+}
+
+struct FinalizeArgs {
+    const void *msm_a, *msm_b2, *msm_l, *msm_h, *msm_b1;   // XYZZ partials (msm_b1 may be null)
+    const void *a0, *b1_0, *b2_0;                            // query[0] points (affine)
+    const void* vk;                                          // alpha_g1 beta_g1 delta_g1 | beta_g2 delta_g2
+    const Fr* rs;                                            // r, s (Montgomery)
+    uint8_t* out;
+};
+
+__global__ void k_prove_finalize(FinalizeArgs f) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const char* vk = reinterpret_cast<const char*>(f.vk);
+    affine_t<Fq> alpha = ldp<affine_t<Fq>>(vk), beta1 = ldp<affine_t<Fq>>(vk + 64), delta1 = ldp<affine_t<Fq>>(vk + 128);
+    affine_t<Fq2> beta2 = ldp<affine_t<Fq2>>(vk + 192), delta2 = ldp<affine_t<Fq2>>(vk + 320);
+    Fr r = Fr::from_mont(f.rs[0]), s = Fr::from_mont(f.rs[1]);
+    Fr rs = Fr::from_mont(Fr::mul(f.rs[0], f.rs[1]));
+    bool r_zero = r.is_zero(), s_zero = s.is_zero();
+
+    xyzz_t<Fq> d1 = xyzz_t<Fq>::from_affine(delta1);
+    xyzz_t<Fq> A = ldp<xyzz_t<Fq>>(f.msm_a);
+    xyzz_t<Fq>::madd(A, ldp<affine_t<Fq>>(f.a0), false);
+    xyzz_t<Fq>::madd(A, alpha, false);
+    if (!r_zero) A = xyzz_t<Fq>::add(A, xyzz_t<Fq>::mul_scalar(d1, r.l));
+
+    xyzz_t<Fq2> Bp = ldp<xyzz_t<Fq2>>(f.msm_b2);
+    xyzz_t<Fq2>::madd(Bp, ldp<affine_t<Fq2>>(f.b2_0), false);
+    xyzz_t<Fq2>::madd(Bp, beta2, false);
+    if (!s_zero) Bp = xyzz_t<Fq2>::add(Bp, xyzz_t<Fq2>::mul_scalar(xyzz_t<Fq2>::from_affine(delta2), s.l));
+
+    xyzz_t<Fq> C = xyzz_t<Fq>::add(ldp<xyzz_t<Fq>>(f.msm_l), ldp<xyzz_t<Fq>>(f.msm_h));
+    if (!s_zero) C = xyzz_t<Fq>::add(C, xyzz_t<Fq>::mul_scalar(A, s.l));
+    if (!r_zero) {
+        xyzz_t<Fq> B1 = ldp<xyzz_t<Fq>>(f.msm_b1);
+        xyzz_t<Fq>::madd(B1, ldp<affine_t<Fq>>(f.b1_0), false);
+        xyzz_t<Fq>::madd(B1, beta1, false);
+        if (!s_zero) B1 = xyzz_t<Fq>::add(B1, xyzz_t<Fq>::mul_scalar(d1, s.l));
+        C = xyzz_t<Fq>::add(C, xyzz_t<Fq>::mul_scalar(B1, r.l));
+        C = xyzz_t<Fq>::add(C, xyzz_t<Fq>::neg(xyzz_t<Fq>::mul_scalar(d1, rs.l)));
+    }
+    compress_g1(A, f.out);
+    compress_g2(Bp, f.out + 32);
+    compress_g1(C, f.out + 96);
+}
+
+int prove_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, const Fr* d_a, const Fr* d_b, const Fr* d_c,
+              const uint64_t r[4], const uint64_t s[4], int mirror_bg1, uint8_t proof_out[128]) {
+    Slot& sl = ctx->slots[0];
+    cudaStream_t st = sl.stream;
+    const size_t n1 = pk->n_vars - 1, n_aux = pk->n_vars - pk->n_inputs, m = pk->m;
+    unsigned log_m = ceil_log2(m);
+    if (((size_t)1 << log_m) != m) return set_error(ctx, B200ZK_ERR_DOMAIN, "h_query length must be a power of two");
+    bool r_nonzero = (r[0] | r[1] | r[2] | r[3]) != 0;
+    bool need_b1 = r_nonzero || mirror_bg1;
+
+    // small device block: 5 partials (3 G1 + 1 G2 + 1 G1) + r,s + 128-byte proof
+    const size_t o_a = 0, o_l = 128, o_h = 256, o_b1 = 384, o_b2 = 512, o_rs = 768, o_out = 832, o_hvec = 1024;
+    B2_CUDA_OK(ctx, sl.small.reserve(o_hvec + m * sizeof(Fr)));
+    char* sm = reinterpret_cast<char*>(sl.small.p);
+    Fr* d_h = reinterpret_cast<Fr*>(sm + o_hvec);
+    uint64_t rs_host[8];
+    memcpy(rs_host, r, 32); memcpy(rs_host + 4, s, 32);
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(sm + o_rs, rs_host, 64, cudaMemcpyHostToDevice, st));
+
+    B2_TRY(h_circom_dev(ctx, sl, d_a, d_b, d_c, log_m, d_h));
+    const char* aq = reinterpret_cast<const char*>(pk->a_query);
+    const char* b1q = reinterpret_cast<const char*>(pk->b_g1_query);
+    const char* b2q = reinterpret_cast<const char*>(pk->b_g2_query);
+    B2_TRY(msm_g1_dev(ctx, sl, aq + 64, d_z + 1, n1, sm + o_a));
+    B2_TRY(msm_g2_dev(ctx, sl, b2q + 128, d_z + 1, n1, sm + o_b2));
+    B2_TRY(msm_g1_dev(ctx, sl, pk->l_query, d_z + pk->n_inputs, n_aux, sm + o_l));
+    B2_TRY(msm_g1_dev(ctx, sl, pk->h_query, d_h, m, sm + o_h));
+    if (need_b1) B2_TRY(msm_g1_dev(ctx, sl, b1q + 64, d_z + 1, n1, sm + o_b1));
+
+    FinalizeArgs f;
+    f.msm_a = sm + o_a; f.msm_b2 = sm + o_b2; f.msm_l = sm + o_l; f.msm_h = sm + o_h;
+    f.msm_b1 = need_b1 ? sm + o_b1 : nullptr;
+    f.a0 = aq; f.b1_0 = b1q; f.b2_0 = b2q;
+    f.vk = pk->vk;
+    f.rs = reinterpret_cast<const Fr*>(sm + o_rs);
+    f.out = reinterpret_cast<uint8_t*>(sm + o_out);
+    {
+        LaunchScope ls(ctx, st, "prove_finalize");
+        k_prove_finalize<<<1, 32, 0, st>>>(f);
+    }
+    B2_TRY(check_launch(ctx, "k_prove_finalize"));
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(proof_out, sm + o_out, 128, cudaMemcpyDeviceToHost, st));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    return B200ZK_OK;
+}
+
+}  // namespace b200zk

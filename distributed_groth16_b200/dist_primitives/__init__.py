@@ -1,0 +1,3 @@
+"""Mirror of the reference crate `dist-primitives` (hot-path part only)."""
+from .dmsm import GroupElement, d_msm  # noqa: F401
+from .dfft import d_fft, d_ifft, fft_in_place_rearrange  # noqa: F401

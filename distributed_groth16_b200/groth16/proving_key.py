@@ -1,0 +1,44 @@
+"""Device-resident proving key -- the vectors `PackedProvingKeyShare{s,u,v,w,h}` carries
+(/root/reference/groth16/src/proving_key.rs:19-25; mapping :48-65: s = a_query[1..], u = h_query,
+w = l_query, h = b_g1_query[1..], v = b_g2_query[1..]) plus the vk points the assembly needs."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from .. import _native
+from ..context import Net, _as_u64, _ptr
+
+
+class ProvingKey:
+    def __init__(self, net: Net, a_query, b_g1_query, b_g2_query, l_query, h_query, n_inputs: int, alpha_g1, beta_g1,
+                 delta_g1, beta_g2, delta_g2):
+        self.net = net
+        aq, b1, lq, hq = (_as_u64(v, 8) for v in (a_query, b_g1_query, l_query, h_query))
+        b2 = _as_u64(b_g2_query, 16)
+        self.n_vars = aq.shape[0]
+        self.n_inputs = int(n_inputs)
+        self.m = hq.shape[0]
+        assert b1.shape[0] == self.n_vars and b2.shape[0] == self.n_vars
+        assert lq.size == 0 or lq.shape[0] == self.n_vars - self.n_inputs
+        vk = np.concatenate([np.asarray(v, dtype=np.uint64).reshape(-1) for v in
+                             (alpha_g1, beta_g1, delta_g1, beta_g2, delta_g2)])
+        assert vk.size == 56
+        self.host = dict(a_query=aq, b_g1_query=b1, b_g2_query=b2, l_query=lq, h_query=hq, vk=vk)
+        h = _native.c_vp()
+        lq_ptr = _ptr(lq) if lq.size else None
+        net.check(net._lib.b200zk_pk_upload(net._h, _ptr(aq), _ptr(b1), _ptr(b2), lq_ptr, _ptr(hq), self.n_vars,
+                                            self.n_inputs, self.m, _ptr(vk), ctypes.byref(h)))
+        self._h = h
+
+    def free(self):
+        if getattr(self, "_h", None) and self.net._h:
+            self.net._lib.b200zk_pk_free(self.net._h, self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

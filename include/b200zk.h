@@ -1,0 +1,133 @@
+/* b200zk.h -- C ABI of the B200-native Groth16 proving hot path (BN254).
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference (100% Rust, CPU only)
+ * has no FFI of its own; each entry point below names the Rust item whose *body* it replaces, and
+ * INTEGRATION.md shows the `extern "C"` block + call-site change a maintainer would add.
+ *
+ * Data layout (identical to arkworks' in-memory representation, so Rust slices can be passed
+ * as-is with `as_ptr() as *const u64`):
+ *   Fr / Fq element : 4 x u64 little-endian limbs, Montgomery form (R = 2^256)
+ *   G1 affine       : x || y                       (8 limbs, 64 B)
+ *   G2 affine       : x.c0 || x.c1 || y.c0 || y.c1 (16 limbs, 128 B)
+ *   infinity        : all-zero coordinates (zkey convention, ark-circom/src/zkey.rs:353-373);
+ *                     result points additionally report it through `*out_is_inf`.
+ * Ownership: the caller owns every host buffer for the duration of the call (borrow semantics
+ * of the Rust slices); the library owns all device memory behind `ctx` / `pk`.
+ * Threading: calls that name different `stream` slots (0..2 = MultiplexedStreamID::{Zero,One,Two},
+ * mpc-net/src/lib.rs:29-33) may be issued concurrently from different host threads, mirroring
+ * `tokio::try_join!` in groth16/src/prove.rs:119-125; calls on one slot are serialised.
+ * There is no CPU fallback: without a CUDA device every entry point fails with B200ZK_ERR_CUDA.
+ */
+#ifndef B200ZK_H
+#define B200ZK_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200zk_ctx b200zk_ctx;
+typedef struct b200zk_pk b200zk_pk;
+
+enum {
+    B200ZK_OK = 0,
+    B200ZK_ERR_LENGTH = 1,  /* bases.len() != scalars.len(): arkworks `Err(min_len)`, surfaced by `?` at dmsm/mod.rs:82 */
+    B200ZK_ERR_DOMAIN = 2,  /* log_n > 28 (Fr two-adicity) / size mismatch: `D::new` -> None, ext_wit.rs:31-32 */
+    B200ZK_ERR_CUDA = 3,
+    B200ZK_ERR_ARG = 4,
+    B200ZK_ERR_OOM = 5
+};
+
+/* ---- context (one per GPU; the reference's per-party `Net` handle plays this role) ---------- */
+int b200zk_ctx_create(int device, b200zk_ctx** out);
+void b200zk_ctx_destroy(b200zk_ctx* ctx);
+const char* b200zk_last_error(const b200zk_ctx* ctx);
+const char* b200zk_version(void);
+/* Make slot `stream` (0..2) launch on a caller-provided cudaStream_t (e.g. torch's current stream). */
+int b200zk_ctx_set_stream(b200zk_ctx* ctx, int stream, void* cuda_stream);
+int b200zk_ctx_sync(b200zk_ctx* ctx, int stream);
+/* Per-kernel CUDA-event profiling (used by bench.py for the roofline numbers). */
+int b200zk_profile_enable(b200zk_ctx* ctx, int on);
+int b200zk_profile_reset(b200zk_ctx* ctx);
+/* Writes a JSON object {"kernel": {"launches": L, "ms": total}, ...} into buf. */
+int b200zk_profile_json(b200zk_ctx* ctx, char* buf, size_t buf_len);
+/* Total kernels launched by this ctx since creation / last reset (bench.py "gpu_launches"). */
+uint64_t b200zk_launch_count(const b200zk_ctx* ctx);
+
+/* ---- d_msm (dist-primitives/src/dmsm/mod.rs:70-98; hot line :82 `G::msm(bases, scalars)`) ---- */
+/* Host buffers.  Returns B200ZK_ERR_LENGTH when n_bases != n_scalars (last_error = min_len). */
+int b200zk_msm_g1(b200zk_ctx* ctx, int stream, const uint64_t* bases, size_t n_bases,
+                  const uint64_t* scalars, size_t n_scalars, uint64_t out_affine[8], int* out_is_inf);
+int b200zk_msm_g2(b200zk_ctx* ctx, int stream, const uint64_t* bases, size_t n_bases,
+                  const uint64_t* scalars, size_t n_scalars, uint64_t out_affine[16], int* out_is_inf);
+/* Device buffers (inputs already resident in HBM).  `d_out_xyzz` receives the un-normalised
+ * partial sum (G1: 4 x 32 B = X,Y,ZZ,ZZZ; G2: 4 x 64 B) so that rank partials can be exchanged
+ * and combined with b200zk_g{1,2}_sum_dev -- the multi-GPU replacement of the king's gather +
+ * `unpackexp` + sum at dmsm/mod.rs:87-97. */
+int b200zk_msm_g1_dev(b200zk_ctx* ctx, int stream, const void* d_bases, const void* d_scalars, size_t n,
+                      void* d_out_xyzz);
+int b200zk_msm_g2_dev(b200zk_ctx* ctx, int stream, const void* d_bases, const void* d_scalars, size_t n,
+                      void* d_out_xyzz);
+/* Sum `count` XYZZ partials (device) and normalise to affine (host). */
+int b200zk_g1_sum_dev(b200zk_ctx* ctx, int stream, const void* d_xyzz, size_t count, uint64_t out_affine[8],
+                      int* out_is_inf);
+int b200zk_g2_sum_dev(b200zk_ctx* ctx, int stream, const void* d_xyzz, size_t count, uint64_t out_affine[16],
+                      int* out_is_inf);
+
+/* ---- d_fft / d_ifft (dist-primitives/src/dfft/mod.rs:17-54 / :56-95) -------------------------- */
+/* In-place on a host buffer of (pad << log_n) x 4 limbs whose first 2^log_n elements are the input:
+ *   out = dom.fft(x) / dom.ifft(x) for `dom = Radix2EvaluationDomain::new(2^log_n)` (natural order
+ *   in and out); coset != 0 uses the coset domain `get_coset(Fr::GENERATOR)` (pss.rs:41-48);
+ *   bitrev_in / bitrev_out apply `fft_in_place_rearrange` (dfft/mod.rs:258-271) to the input / to the
+ *   (padded) output -- the `rearrange` flag; pad >= 1 zero-extends the result to pad * 2^log_n
+ *   before the output rearrangement (dfft/mod.rs:225-227). */
+int b200zk_ntt_fr(b200zk_ctx* ctx, int stream, uint64_t* data, unsigned log_n, int inverse, int coset,
+                  int bitrev_in, int bitrev_out, unsigned pad);
+/* Device-resident, natural order, out-of-place allowed (d_out may equal d_in); batch contiguous. */
+int b200zk_ntt_fr_dev(b200zk_ctx* ctx, int stream, const void* d_in, void* d_out, unsigned log_n, int inverse,
+                      int coset, unsigned batch);
+/* Building blocks of the multi-GPU four-step NTT; see parallel.py for the orchestration:
+ * column transform of a [rows x cols] slab along `rows` with twiddle w_N^(global_col*k) applied. */
+int b200zk_ntt_fr_fourstep_cols_dev(b200zk_ctx* ctx, int stream, const void* d_in, void* d_out, unsigned log_rows,
+                                    unsigned log_cols_local, unsigned log_n, uint64_t global_col0, int inverse);
+
+/* ---- ext_wit::h (groth16/src/ext_wit.rs:16-101 == ark-circom/src/circom/qap.rs:64-89) --------- */
+/* a, b, c: QAP evaluation vectors (2^log_m x 4 limbs each); h_out[i] = A(w^(2i+1)) B(..) - C(..). */
+int b200zk_h_circom(b200zk_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* c, unsigned log_m,
+                    uint64_t* h_out);
+int b200zk_h_circom_dev(b200zk_ctx* ctx, const void* d_a, const void* d_b, const void* d_c, unsigned log_m,
+                        void* d_h_out);
+
+/* ---- proving key (what PackedProvingKeyShare carries, groth16/src/proving_key.rs:19-25,48-65) -- */
+/* a_query, b_g1_query, b_g2_query: n_vars points; l_query: n_vars - n_inputs; h_query: m points.
+ * vk_points = alpha_g1(8) beta_g1(8) delta_g1(8) beta_g2(16) delta_g2(16) limbs. */
+int b200zk_pk_upload(b200zk_ctx* ctx, const uint64_t* a_query, const uint64_t* b_g1_query,
+                     const uint64_t* b_g2_query, const uint64_t* l_query, const uint64_t* h_query, size_t n_vars,
+                     size_t n_inputs, size_t m, const uint64_t* vk_points, b200zk_pk** out);
+void b200zk_pk_free(b200zk_ctx* ctx, b200zk_pk* pk);
+
+/* ---- prove::{A,B,C}::compute + assembly (groth16/src/prove.rs:21-136, examples/sha256.rs:208-212)
+ * z: full assignment (n_vars x 4 limbs, z[0] = 1); a, b, c: QAP evaluation vectors (m x 4 limbs);
+ * r, s: 4 limbs (Montgomery; the reference always passes zero).  mirror_bg1 != 0 also runs the
+ * MSM over b_g1_query when r == 0, as the reference does unconditionally (prove.rs:123).
+ * proof_out: Proof<Bn254> in ark-serialize Compress::Yes form (A 32 || B 64 || C 32 bytes). */
+int b200zk_groth16_prove(b200zk_ctx* ctx, const b200zk_pk* pk, const uint64_t* z, const uint64_t* a,
+                         const uint64_t* b, const uint64_t* c, const uint64_t r[4], const uint64_t s[4],
+                         int mirror_bg1, uint8_t proof_out[128]);
+
+/* ---- deterministic dummy inputs (groth16/examples/local_groth_bench.rs:21-52,
+ *      groth16/src/proving_key.rs:112-155 generate dummy CRS points the same way: not a setup) ---- */
+int b200zk_g1_generate_dev(b200zk_ctx* ctx, uint64_t seed, size_t n, void* d_out);
+int b200zk_g2_generate_dev(b200zk_ctx* ctx, uint64_t seed, size_t n, void* d_out);
+int b200zk_fr_generate_dev(b200zk_ctx* ctx, uint64_t seed, size_t n, void* d_out);
+
+/* ---- self-test hooks (tests only): element-wise field ops on device ------------------------- */
+/* op: 0 mul, 1 add, 2 sub; field: 0 Fq, 1 Fr.  a, b, out: n x 4 limbs host buffers. */
+int b200zk_test_field_op(b200zk_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out,
+                         size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ZK_H */

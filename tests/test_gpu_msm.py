@@ -1,0 +1,119 @@
+"""d_msm parity: CUDA Pippenger (csrc/msm.cu) vs the oracle, through the C ABI.
+
+Mirrors dist-primitives/examples/dmsm_test.rs:49-64 (d_msm == G::msm on the public vectors) and
+dmsm/mod.rs:147-193 (all scalars = 1), instantiated for BN254 as BASELINE config 1 asks."""
+import numpy as np
+import pytest
+
+from distributed_groth16_b200 import MpcNetError
+from distributed_groth16_b200.dist_primitives import d_msm
+
+pytestmark = pytest.mark.gpu
+
+
+def _limbs(v):
+    return [(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)]
+
+
+def _check(net, cref, bases, scalars, g2):
+    got = d_msm(bases, scalars, None, net)
+    exp, inf = (cref.msm_g2 if g2 else cref.msm_g1)(bases, scalars)
+    assert got.infinity == inf
+    assert (got.limbs == exp).all()
+    return got
+
+
+@pytest.mark.parametrize("g2", [False, True])
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 100, 1000])
+def test_small_sizes(net, cref, n, g2):
+    bases = (cref.g2_generate if g2 else cref.g1_generate)(0xB2000001, n)
+    scalars = cref.fr_generate(42 + n, n)
+    _check(net, cref, bases, scalars, g2)
+
+
+@pytest.mark.parametrize("g2", [False, True])
+def test_config1_4096_with_edge_cases(net, cref, g2):
+    """BASELINE config 1: 2^12 pairs + forced edge cases (0, 1, r-1, 2^253, duplicates, P and -P, infinity base)."""
+    from oracle import layout, bn254 as o
+    n = 4096
+    bases = (cref.g2_generate if g2 else cref.g1_generate)(0xB2000001, n)
+    scalars = cref.fr_generate(0xB2000001, n)
+    sc = layout.fr_to_arr([0, 1, o.R - 1, 1 << 253, 5, 5, 7, 7, 9])
+    scalars[:9] = sc
+    w = bases.shape[1]
+    bases[4] = bases[5]                                   # duplicate point, same scalar -> P + P inside a bucket
+    pts = (layout.arr_to_g2 if g2 else layout.arr_to_g1)(bases[6:7])
+    neg = (o.G2 if g2 else o.G1).neg(pts[0])
+    bases[7] = (layout.g2_to_arr if g2 else layout.g1_to_arr)([neg])[0]   # P and -P with the same scalar -> cancels
+    bases[8] = np.zeros(w, dtype=np.uint64)               # infinity base (zkey convention)
+    _check(net, cref, bases, scalars, g2)
+
+
+@pytest.mark.parametrize("g2", [False, True])
+def test_all_scalars_one_and_all_zero(net, cref, g2):
+    """dmsm/mod.rs:173-193 uses scalars = 1 for every base."""
+    from oracle import layout
+    n = 256
+    bases = (cref.g2_generate if g2 else cref.g1_generate)(3, n)
+    _check(net, cref, bases, layout.fr_to_arr([1] * n), g2)
+    got = _check(net, cref, bases, layout.fr_to_arr([0] * n), g2)
+    assert got.infinity
+
+
+def test_skewed_witness_like_scalars(net, cref):
+    """Real witnesses are mostly 0/1/small: giant buckets must still give the right point."""
+    from oracle import layout
+    n = 5000
+    rng = np.random.default_rng(5)
+    vals = [int(v) for v in rng.choice([0, 1, 1, 1, 2, 3, 255, 65535], size=n)]
+    bases = cref.g1_generate(9, n)
+    _check(net, cref, bases, layout.fr_to_arr(vals), False)
+
+
+def test_empty_and_length_mismatch(net, cref):
+    bases = cref.g1_generate(1, 8)
+    scalars = cref.fr_generate(1, 8)
+    got = d_msm(bases[:0], scalars[:0], None, net, g2=False)
+    assert got.infinity
+    with pytest.raises(MpcNetError) as ei:
+        d_msm(bases, scalars[:5], None, net)
+    assert ei.value.kind == "Generic" and ei.value.message == "5"     # arkworks Err(min_len) -> to_string()
+
+
+def test_g1_2_16_vs_oracle(net, cref):
+    n = 1 << 16
+    bases = cref.g1_generate(0xB2000002, n)
+    scalars = cref.fr_generate(0xB2000002, n)
+    _check(net, cref, bases, scalars, False)
+
+
+def test_generator_kernels_match_oracle(net, cref):
+    g1 = net.generate_g1(123, 300).cpu().numpy().view(np.uint64)
+    g2 = net.generate_g2(123, 100).cpu().numpy().view(np.uint64)
+    fr = net.generate_fr(123, 1000).cpu().numpy().view(np.uint64)
+    assert (g1 == cref.g1_generate(123, 300)).all()
+    assert (g2 == cref.g2_generate(123, 100)).all()
+    assert (fr == cref.fr_generate(123, 1000)).all()
+
+
+def test_config2_g1_2_20_device_resident(net, cref):
+    """BASELINE config 2: 2^20 pairs, inputs generated and kept in HBM; oracle on the same inputs."""
+    import torch
+    n = 1 << 20
+    bases = net.generate_g1(0xB2000002, n)
+    scalars = net.generate_fr(0xB2000002, n)
+    got = d_msm(bases, scalars, None, net)
+    bh = bases.cpu().numpy().view(np.uint64)
+    sh = scalars.cpu().numpy().view(np.uint64)
+    assert cref.g1_on_curve(bh[:4096])
+    exp, inf = cref.msm_g1(bh, sh)
+    assert not inf and (got.limbs == exp).all()
+    # linearity: MSM(P, s) + MSM(P, t) == MSM(P, s + t)
+    t = net.generate_fr(77, n)
+    st = torch.from_numpy(net.field_op(1, 1, sh, t.cpu().numpy().view(np.uint64)).view(np.int64)).to(bases.device)
+    lhs = d_msm(bases, st, None, net)
+    part = d_msm(bases, t, None, net)
+    both = np.stack([got.limbs, part.limbs])
+    from oracle import layout
+    exp_sum, _ = cref.msm_g1(both, layout.fr_to_arr([1, 1]))
+    assert (lhs.limbs == exp_sum).all()

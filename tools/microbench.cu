@@ -1,0 +1,133 @@
+// tools/microbench.cu -- instruction-throughput probes used to choose the field-multiplier schedule.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench tools/microbench.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "../distributed_groth16_b200/csrc/ec.cuh"
+using namespace b200zk;
+
+#define ITERS 2000
+
+__global__ void k_imad(uint32_t* out, uint32_t a, uint32_t b) {
+    uint32_t r[8];
+    for (int i = 0; i < 8; ++i) r[i] = threadIdx.x + i;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(a), "r"(b));
+    }
+    uint32_t s = 0; for (int i = 0; i < 8; ++i) s += r[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void k_imad_hi(uint32_t* out, uint32_t a, uint32_t b) {
+    uint32_t r[8];
+    for (int i = 0; i < 8; ++i) r[i] = threadIdx.x + i;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(a), "r"(b));
+    }
+    uint32_t s = 0; for (int i = 0; i < 8; ++i) s += r[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void k_imad_wide(uint64_t* out, uint32_t a, uint32_t b) {
+    uint64_t r[8];
+    for (int i = 0; i < 8; ++i) r[i] = threadIdx.x + i;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(r[i]) : "r"(a + i), "r"(b));
+    }
+    uint64_t s = 0; for (int i = 0; i < 8; ++i) s += r[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// 4 fused (lo.cc, hi.cc) pairs in one carry chain = 4 IMAD.WIDE.U32(.X) per "op group"
+__global__ void k_imad_wide_cc(uint32_t* out, uint32_t a, uint32_t b) {
+    uint32_t r[8];
+    for (int i = 0; i < 8; ++i) r[i] = threadIdx.x + i;
+    for (int it = 0; it < ITERS; ++it) {
+        asm volatile(
+            "mad.lo.cc.u32 %0, %8, %9, %0;\n\tmadc.hi.cc.u32 %1, %8, %9, %1;\n\t"
+            "madc.lo.cc.u32 %2, %10, %9, %2;\n\tmadc.hi.cc.u32 %3, %10, %9, %3;\n\t"
+            "madc.lo.cc.u32 %4, %11, %9, %4;\n\tmadc.hi.cc.u32 %5, %11, %9, %5;\n\t"
+            "madc.lo.cc.u32 %6, %12, %9, %6;\n\tmadc.hi.u32 %7, %12, %9, %7;"
+            : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+            : "r"(a), "r"(b), "r"(a + 1), "r"(a + 2), "r"(a + 3));
+    }
+    uint32_t s = 0; for (int i = 0; i < 8; ++i) s += r[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void k_iadd3(uint32_t* out, uint32_t a, uint32_t b) {
+    uint32_t r[8];
+    for (int i = 0; i < 8; ++i) r[i] = threadIdx.x + i;
+    for (int it = 0; it < ITERS; ++it) {
+        asm volatile(
+            "add.cc.u32 %0, %0, %8;\n\taddc.cc.u32 %1, %1, %9;\n\taddc.cc.u32 %2, %2, %8;\n\taddc.cc.u32 %3, %3, %9;\n\t"
+            "addc.cc.u32 %4, %4, %8;\n\taddc.cc.u32 %5, %5, %9;\n\taddc.cc.u32 %6, %6, %8;\n\taddc.u32 %7, %7, %9;"
+            : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+            : "r"(a), "r"(b));
+    }
+    uint32_t s = 0; for (int i = 0; i < 8; ++i) s += r[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void k_mul_chain(Fq* out, int iters) {
+    Fq x = Fq::one(), y = Fq::one();
+    x.l[0] += threadIdx.x; y.l[1] += blockIdx.x + 3;
+    for (int it = 0; it < iters; ++it) x = Fq::mul(x, y);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x;
+}
+__global__ void k_mul_chain2(Fq* out, int iters) {   // two independent chains per thread (ILP)
+    Fq x = Fq::one(), y = Fq::one(), z = Fq::one();
+    x.l[0] += threadIdx.x; y.l[1] += blockIdx.x + 3; z.l[2] += threadIdx.x * 7;
+    for (int it = 0; it < iters; ++it) { x = Fq::mul(x, y); z = Fq::mul(z, y); }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = Fq::add(x, z);
+}
+__global__ void __launch_bounds__(128) k_madd_chain(xyzz_t<Fq>* out, int iters) {
+    affine_t<Fq> p;
+    for (int i = 0; i < 8; ++i) { p.x.l[i] = CurveConst::g1_gen_x(i); p.y.l[i] = CurveConst::g1_gen_y(i); }
+    xyzz_t<Fq> acc = xyzz_t<Fq>::dbl_affine(p.x, p.y);
+    acc.x.l[0] ^= 0;   // keep
+    for (int it = 0; it < iters; ++it) xyzz_t<Fq>::madd(acc, p, (it & 1) && false);
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+template <class K>
+static float timeit(K launch) {
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    launch(); cudaDeviceSynchronize();
+    cudaEventRecord(a); launch(); cudaEventRecord(b); cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b); return ms;
+}
+
+int main() {
+    cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
+    int sms = p.multiProcessorCount;
+    printf("device %s, %d SMs, clock %d kHz\n", p.name, sms, p.clockRate);
+    void* buf; cudaMalloc(&buf, (size_t)sms * 8 * 1024 * 256);
+    int blocks = sms * 8, threads = 256;
+    double nthreads = (double)blocks * threads;
+    float ms;
+    ms = timeit([&] { k_imad<<<blocks, threads>>>((uint32_t*)buf, 3, 5); });
+    printf("IMAD            : %.3f ms  %.2f Tops/s  (%.1f lanes/clk/SM @1.9GHz)\n", ms, nthreads * ITERS * 8 / ms / 1e9, nthreads * ITERS * 8 / (ms * 1e-3) / sms / 1.9e9);
+    ms = timeit([&] { k_imad_hi<<<blocks, threads>>>((uint32_t*)buf, 3, 5); });
+    printf("IMAD.HI         : %.3f ms  %.2f Tops/s  (%.1f lanes/clk/SM)\n", ms, nthreads * ITERS * 8 / ms / 1e9, nthreads * ITERS * 8 / (ms * 1e-3) / sms / 1.9e9);
+    ms = timeit([&] { k_imad_wide<<<blocks, threads>>>((uint64_t*)buf, 3, 5); });
+    printf("IMAD.WIDE       : %.3f ms  %.2f Tops/s  (%.1f lanes/clk/SM)\n", ms, nthreads * ITERS * 8 / ms / 1e9, nthreads * ITERS * 8 / (ms * 1e-3) / sms / 1.9e9);
+    ms = timeit([&] { k_imad_wide_cc<<<blocks, threads>>>((uint32_t*)buf, 3, 5); });
+    printf("IMAD.WIDE.X x4  : %.3f ms  %.2f T wide-ops/s  (%.1f lanes/clk/SM)\n", ms, nthreads * ITERS * 4 / ms / 1e9, nthreads * ITERS * 4 / (ms * 1e-3) / sms / 1.9e9);
+    ms = timeit([&] { k_iadd3<<<blocks, threads>>>((uint32_t*)buf, 3, 5); });
+    printf("IADD3(.X) x8    : %.3f ms  %.2f Tops/s  (%.1f lanes/clk/SM)\n", ms, nthreads * ITERS * 8 / ms / 1e9, nthreads * ITERS * 8 / (ms * 1e-3) / sms / 1.9e9);
+    int iters = 2000;
+    for (int t : {64, 128, 256, 512}) {
+        int bl = sms * (2048 / t > 16 ? 16 : 2048 / t);
+        ms = timeit([&] { k_mul_chain<<<bl, t>>>((Fq*)buf, iters); });
+        printf("Fq::mul chain   : blocks %d x %d thr: %.3f ms  %.1f Gmul/s\n", bl, t, ms, (double)bl * t * iters / ms / 1e6);
+    }
+    ms = timeit([&] { k_mul_chain2<<<sms * 4, 256>>>((Fq*)buf, iters); });
+    printf("Fq::mul 2chains : %.3f ms  %.1f Gmul/s\n", ms, (double)sms * 4 * 256 * iters * 2 / ms / 1e6);
+    ms = timeit([&] { k_mul_chain<<<1, 32>>>((Fq*)buf, iters); });
+    printf("Fq::mul latency : single warp: %.1f ns per dependent mul\n", ms * 1e6 / iters);
+    ms = timeit([&] { k_madd_chain<<<sms * 4, 128>>>((xyzz_t<Fq>*)buf, 500); });
+    printf("madd chain      : %.3f ms  %.2f Gmadd/s\n", ms, (double)sms * 4 * 128 * 500 / ms / 1e6);
+    ms = timeit([&] { k_madd_chain<<<sms * 8, 128>>>((xyzz_t<Fq>*)buf, 500); });
+    printf("madd chain x2occ: %.3f ms  %.2f Gmadd/s\n", ms, (double)sms * 8 * 128 * 500 / ms / 1e6);
+    ms = timeit([&] { k_madd_chain<<<1, 32>>>((xyzz_t<Fq>*)buf, 500); });
+    printf("madd latency    : single warp: %.1f ns per dependent madd\n", ms * 1e6 / 500);
+    return 0;
+}
