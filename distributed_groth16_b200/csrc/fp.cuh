@@ -27,6 +27,14 @@
 #define B2_HD_NI inline
 #endif
 
+// build-time experiment switches (tools/variants.sh): multiplier schedule and inlining
+#ifndef B2_MUL_VARIANT
+#define B2_MUL_VARIANT 1      // 0: mad.lo.cc/madc.hi.cc rows everywhere; 1: IMAD.WIDE + IADD3 chains for the a*b rows
+#endif
+#ifndef B2_MUL_NOINLINE
+#define B2_MUL_NOINLINE 0     // 1: Fp::mul is an out-of-line call (small I-cache footprint)
+#endif
+
 namespace b200zk {
 
 // ---------------------------------------------------------------------------------------------
@@ -171,8 +179,21 @@ struct Fp {
         acc[6] = cc::madc_lo_cc(a[6], bi, 0);
         acc[7] = cc::madc_hi(a[6], bi, 0);
     }
+    // 64-bit products of the even-indexed limbs of a with bi: t[j], t[j+1] = a[j]*bi (plain IMAD.WIDE,
+    // full rate on sm_100a; the carry-in/out form of IMAD.WIDE issues at half rate, measured with
+    // tools/microbench.cu, so the a*b rows add their products with IADD3 chains on the ALU pipe while
+    // the m*p rows keep the fused carry form on the FMA pipe -- the two pipes then overlap).
+    B2_HD static void prod_n(uint32_t* t, const uint32_t* a, uint32_t bi) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            uint64_t w = (uint64_t)a[j] * bi;
+            t[j] = (uint32_t)w;
+            t[j + 1] = (uint32_t)(w >> 32);
+        }
+    }
     // one row: (ev + 2^32 od) <- (ev + 2^32 od + a*bi + m*p) / 2^32, roles of ev/od swap for the next row
     B2_HD static void mad_row(uint32_t* ev, uint32_t* od, const uint32_t* a, uint32_t bi, bool first) {
+#if B2_MUL_VARIANT == 0
         if (first) {
             mul_n(od, a + 1, bi);
             mul_n(ev, a, bi);
@@ -182,12 +203,37 @@ struct Fp {
             cmad_n(ev, a, bi);
             od[7] = cc::addc(od[7], 0);
         }
+#else
+        if (first) {
+            prod_n(od, a + 1, bi);
+            prod_n(ev, a, bi);
+        } else {
+            uint32_t te[8], to[8];
+            prod_n(to, a + 1, bi);
+            prod_n(te, a, bi);
+            ev[0] = cc::add_cc(ev[0], od[1]);
+#pragma unroll
+            for (int j = 0; j < 6; ++j) od[j] = cc::addc_cc(od[j + 2], to[j]);      // od = (od >> 64) + to + carry
+            od[6] = cc::addc_cc(to[6], 0);
+            od[7] = cc::addc(to[7], 0);                                           // a[7]*bi < 2^62: no carry out
+            ev[0] = cc::add_cc(ev[0], te[0]);
+#pragma unroll
+            for (int j = 1; j < 8; ++j) ev[j] = cc::addc_cc(ev[j], te[j]);
+            od[7] = cc::addc(od[7], 0);
+        }
+#endif
         uint32_t mi = ev[0] * P::INV;
         cmad_mod<1>(od, mi);
         cmad_mod<0>(ev, mi);
         od[7] = cc::addc(od[7], 0);
     }
+#if B2_MUL_NOINLINE && defined(__CUDA_ARCH__)
+    B2_HD static Fp mul(const Fp& a, const Fp& b) { return mul_ni(a, b); }
+    B2_HD static Fp mul_inl(const Fp& a, const Fp& b) {
+#else
+    B2_HD static Fp mul_inl(const Fp& a, const Fp& b) { return mul(a, b); }
     B2_HD static Fp mul(const Fp& a, const Fp& b) {
+#endif
         uint32_t ev[8], od[8];
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {
@@ -203,7 +249,7 @@ struct Fp {
     B2_HD static Fp sqr(const Fp& a) { return mul(a, a); }
     // out-of-line copy for the cold / very large kernels (G2, reductions): keeps code size and
     // compile time bounded; the G1 bucket loop uses the inlined `mul`.
-    B2_HD_NI static Fp mul_ni(const Fp& a, const Fp& b) { return mul(a, b); }
+    B2_HD_NI static Fp mul_ni(const Fp& a, const Fp& b) { return mul_inl(a, b); }
 
     B2_HD static Fp to_mont(const Fp& a) { return mul(a, r2()); }
     B2_HD static Fp from_mont(const Fp& a) {

@@ -154,80 +154,147 @@ __global__ void k_msm_scatter(const uint32_t* keys, const uint32_t* ranks, const
 }
 
 // ---------------------------------------------------------------------------------------------
-// 4. bucket accumulation
+// 4. bucket accumulation over bounded-size tasks
+//    A bucket of s entries is cut into ceil(s / TASK_LEN) tasks, so a "giant" bucket (the short top
+//    window, or the digit-1 bucket of a 0/1-heavy witness) is spread over many threads instead of
+//    serialising one.  Single-task buckets write their sum straight into buckets[g]; the rare
+//    multi-task buckets go through task_sums[] and a block-level merge.
 // ---------------------------------------------------------------------------------------------
-template <class F>
-__global__ void __launch_bounds__(128) k_msm_accumulate(const affine_t<F>* bases, const uint32_t* entries, const uint32_t* offsets,
-                                 uint32_t nbuckets, xyzz_t<F>* buckets) {
+static const uint32_t TASK_LEN = 128;
+#ifndef B2_ACC_MINBLOCKS
+#define B2_ACC_MINBLOCKS 4
+#endif
+
+__global__ void k_msm_task_counts(const uint32_t* offsets, uint32_t nbuckets, uint32_t* ntasks) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > nbuckets) return;
+    ntasks[g] = g < nbuckets ? (offsets[g + 1] - offsets[g] + TASK_LEN - 1) / TASK_LEN : 0;
+}
+
+// task_bucket[t] = owning bucket; buckets with > 1 task are appended to multi_list
+__global__ void k_msm_fill_tasks(const uint32_t* task_off, uint32_t nbuckets, uint32_t* task_bucket, uint32_t* multi_list,
+                                 uint32_t* multi_count) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= nbuckets) return;
-    uint32_t lo = offsets[g], hi = offsets[g + 1];
+    uint32_t lo = task_off[g], hi = task_off[g + 1];
+    for (uint32_t t = lo; t < hi; ++t) task_bucket[t] = g;
+    if (hi - lo > 1) multi_list[atomicAdd(multi_count, 1u)] = g;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128, B2_ACC_MINBLOCKS) k_msm_accumulate(const affine_t<F>* bases, const uint32_t* entries, const uint32_t* offsets,
+                                 const uint32_t* task_off, const uint32_t* task_bucket, uint32_t nbuckets,
+                                 xyzz_t<F>* buckets, xyzz_t<F>* task_sums) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= task_off[nbuckets]) return;
+    uint32_t g = task_bucket[t];
+    uint32_t t0 = task_off[g], nt = task_off[g + 1] - t0;
+    uint32_t lo = offsets[g] + (t - t0) * TASK_LEN, end = offsets[g + 1];
+    uint32_t hi = lo + TASK_LEN < end ? lo + TASK_LEN : end;
     xyzz_t<F> acc = xyzz_t<F>::identity();
     for (uint32_t k = lo; k < hi; ++k) {
         uint32_t e = entries[k];
         affine_t<F> p = ld16(bases + (e & 0x7FFFFFFFu));
         xyzz_t<F>::madd(acc, p, (e >> 31) != 0);
     }
-    st16(buckets + g, acc);
+    if (nt == 1) st16(buckets + g, acc);
+    else st16(task_sums + t, acc);
+}
+
+// buckets[g] = sum of the task sums of g, for every multi-task bucket; one block (32 quads) per bucket, grid-strided
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_merge_tasks(const uint32_t* multi_list, const uint32_t* multi_count,
+                                  const uint32_t* task_off, const xyzz_t<F>* task_sums, xyzz_t<F>* buckets) {
+    typedef quad_ops<F> Q;
+    __shared__ xyzz_t<F> sh[32];
+    const uint32_t qid = threadIdx.x >> 2, ql = threadIdx.x & 3;
+    uint32_t cnt = *multi_count;
+    for (uint32_t i = blockIdx.x; i < cnt; i += gridDim.x) {
+        uint32_t g = multi_list[i];
+        uint32_t lo = task_off[g], hi = task_off[g + 1];
+        xyzz_t<F> acc = xyzz_t<F>::identity();
+        for (uint32_t t = lo + qid; t < hi; t += 32) acc = Q::add(acc, ld16(task_sums + t));
+        if (ql == 0) sh[qid] = acc;
+        __syncthreads();
+        for (int s = 16; s > 0; s >>= 1) {
+            if ((int)qid < s) {
+                xyzz_t<F> a = sh[qid], b = sh[qid + s];
+                a = Q::add(a, b);
+                __syncwarp(Q::quad_mask());
+                if (ql == 0) sh[qid] = a;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) st16(buckets + g, sh[0]);
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
 // 5. window reduction: S_w = sum_{k<B} (k+1) * bucket[w][k]
 // ---------------------------------------------------------------------------------------------
+// one quad (4 lanes, quad_ops) per (window, segment)
 template <class F>
 __global__ void __launch_bounds__(128) k_msm_reduce_segments(const xyzz_t<F>* buckets, uint32_t W, uint32_t B, uint32_t seg_len,
                                       xyzz_t<F>* partials) {
+    typedef quad_ops<F> Q;
     uint32_t nseg = B / seg_len;
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     if (t >= W * nseg) return;
     uint32_t w = t / nseg, seg = t % nseg;
     uint32_t lo = seg * seg_len;
     const xyzz_t<F>* bw = buckets + (size_t)w * B;
     xyzz_t<F> run = xyzz_t<F>::identity(), acc = xyzz_t<F>::identity();
     for (uint32_t k = lo + seg_len; k-- > lo;) {
-        run = xyzz_t<F>::add(run, ld16(bw + k));
-        acc = xyzz_t<F>::add(acc, run);
+        run = Q::add(run, ld16(bw + k));
+        acc = Q::add(acc, run);
     }
     if (lo) {   // + lo * run
         xyzz_t<F> m = xyzz_t<F>::identity();
         for (int bit = 31 - __clz(lo); bit >= 0; --bit) {
-            m = xyzz_t<F>::dbl(m);
-            if ((lo >> bit) & 1) m = xyzz_t<F>::add(m, run);
+            m = Q::dbl(m);
+            if ((lo >> bit) & 1) m = Q::add(m, run);
         }
-        acc = xyzz_t<F>::add(acc, m);
+        acc = Q::add(acc, m);
     }
-    st16(partials + t, acc);
+    if ((threadIdx.x & 3) == 0) st16(partials + t, acc);
 }
 
-// one block per window: sum nseg partials
+// one block per window: sum nseg partials (THREADS / 4 quads)
 template <class F, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_msm_window_sum(const xyzz_t<F>* partials, uint32_t nseg, xyzz_t<F>* wsum) {
-    __shared__ xyzz_t<F> sh[THREADS];
+    typedef quad_ops<F> Q;
+    constexpr int NQ = THREADS / 4;
+    __shared__ xyzz_t<F> sh[NQ];
+    const uint32_t qid = threadIdx.x >> 2, ql = threadIdx.x & 3;
     const xyzz_t<F>* p = partials + (size_t)blockIdx.x * nseg;
     xyzz_t<F> acc = xyzz_t<F>::identity();
-    for (uint32_t i = threadIdx.x; i < nseg; i += THREADS) acc = xyzz_t<F>::add(acc, ld16(p + i));
-    sh[threadIdx.x] = acc;
+    for (uint32_t i = qid; i < nseg; i += NQ) acc = Q::add(acc, ld16(p + i));
+    if (ql == 0) sh[qid] = acc;
     __syncthreads();
-    for (int s = THREADS / 2; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) {
-            xyzz_t<F> a = sh[threadIdx.x], b = sh[threadIdx.x + s];
-            sh[threadIdx.x] = xyzz_t<F>::add(a, b);
+    for (int s = NQ / 2; s > 0; s >>= 1) {
+        if ((int)qid < s) {
+            xyzz_t<F> a = sh[qid], b = sh[qid + s];
+            a = Q::add(a, b);
+            __syncwarp(Q::quad_mask());
+            if (ql == 0) sh[qid] = a;
         }
         __syncthreads();
     }
     if (threadIdx.x == 0) st16(wsum + blockIdx.x, sh[0]);
 }
 
-// 6. Horner over windows
+// 6. Horner over windows (one quad)
 template <class F>
 __global__ void k_msm_combine(const xyzz_t<F>* wsum, uint32_t W, uint32_t c, xyzz_t<F>* out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    typedef quad_ops<F> Q;
+    if (threadIdx.x >= 4 || blockIdx.x != 0) return;
     xyzz_t<F> total = ld16(wsum + (W - 1));
     for (int w = (int)W - 2; w >= 0; --w) {
-        for (uint32_t k = 0; k < c; ++k) total = xyzz_t<F>::dbl(total);
-        total = xyzz_t<F>::add(total, ld16(wsum + w));
+        for (uint32_t k = 0; k < c; ++k) total = Q::dbl(total);
+        total = Q::add(total, ld16(wsum + w));
     }
-    st16(out, total);
+    if (threadIdx.x == 0) st16(out, total);
 }
 
 // sum `count` XYZZ points, normalise; out = affine followed by one u64 infinity flag
@@ -303,7 +370,13 @@ static int msm_dev_impl(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const vo
     size_t o_counts = o_entries + al(total * 4);
     size_t o_offsets = o_counts + al(((size_t)nb + 1) * 4);
     size_t o_sums = o_offsets + al(((size_t)nb + 1) * 4);
-    size_t o_buckets = o_sums + al(((size_t)nb / SCAN_TILE + 2) * 4);
+    const size_t max_tasks = total / TASK_LEN + nb + 1;
+    size_t o_ntasks = o_sums + al(((size_t)nb / SCAN_TILE + 2) * 4);
+    size_t o_taskoff = o_ntasks + al(((size_t)nb + 1) * 4);
+    size_t o_taskbucket = o_taskoff + al(((size_t)nb + 1) * 4);
+    size_t o_multi = o_taskbucket + al(max_tasks * 4);
+    size_t o_tasksums = o_multi + al((total / TASK_LEN + 2) * 4);
+    size_t o_buckets = o_tasksums + al(max_tasks * sizeof(xyzz_t<F>));
     size_t o_partials = o_buckets + al((size_t)nb * sizeof(xyzz_t<F>));
     size_t o_wsum = o_partials + al((size_t)W * nseg * sizeof(xyzz_t<F>));
     size_t ws_bytes = o_wsum + al((size_t)W * sizeof(xyzz_t<F>));
@@ -315,6 +388,11 @@ static int msm_dev_impl(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const vo
     uint32_t* counts = reinterpret_cast<uint32_t*>(ws + o_counts);
     uint32_t* offsets = reinterpret_cast<uint32_t*>(ws + o_offsets);
     uint32_t* sums = reinterpret_cast<uint32_t*>(ws + o_sums);
+    uint32_t* ntasks = reinterpret_cast<uint32_t*>(ws + o_ntasks);
+    uint32_t* task_off = reinterpret_cast<uint32_t*>(ws + o_taskoff);
+    uint32_t* task_bucket = reinterpret_cast<uint32_t*>(ws + o_taskbucket);
+    uint32_t* multi = reinterpret_cast<uint32_t*>(ws + o_multi);       // [0] = count, [1..] = list
+    xyzz_t<F>* task_sums = reinterpret_cast<xyzz_t<F>*>(ws + o_tasksums);
     xyzz_t<F>* buckets = reinterpret_cast<xyzz_t<F>*>(ws + o_buckets);
     xyzz_t<F>* partials = reinterpret_cast<xyzz_t<F>*>(ws + o_partials);
     xyzz_t<F>* wsum = reinterpret_cast<xyzz_t<F>*>(ws + o_wsum);
@@ -328,30 +406,48 @@ static int msm_dev_impl(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const vo
     B2_TRY(check_launch(ctx, "k_msm_digits"));
     B2_TRY(exclusive_scan(ctx, st, counts, offsets, sums, nb + 1));
     {
+        LaunchScope ls(ctx, st, "msm_tasks");
+        k_msm_task_counts<<<(nb + 1 + 255) / 256, 256, 0, st>>>(offsets, nb, ntasks);
+    }
+    B2_TRY(check_launch(ctx, "k_msm_task_counts"));
+    B2_TRY(exclusive_scan(ctx, st, ntasks, task_off, sums, nb + 1));
+    B2_CUDA_OK(ctx, cudaMemsetAsync(multi, 0, 4, st));
+    B2_CUDA_OK(ctx, cudaMemsetAsync(buckets, 0, (size_t)nb * sizeof(xyzz_t<F>), st));   // all-zero XYZZ = identity
+    {
+        LaunchScope ls(ctx, st, "msm_tasks");
+        k_msm_fill_tasks<<<(nb + 255) / 256, 256, 0, st>>>(task_off, nb, task_bucket, multi + 1, multi);
+    }
+    B2_TRY(check_launch(ctx, "k_msm_fill_tasks"));
+    {
         LaunchScope ls(ctx, st, "msm_scatter");
         k_msm_scatter<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(keys, ranks, offsets, (uint32_t)n, total, entries);
     }
     B2_TRY(check_launch(ctx, "k_msm_scatter"));
     {
         LaunchScope ls(ctx, st, acc_name);
-        k_msm_accumulate<F><<<(nb + 127) / 128, 128, 0, st>>>(reinterpret_cast<const affine_t<F>*>(d_bases), entries, offsets,
-                                                               nb, buckets);
+        k_msm_accumulate<F><<<(unsigned)((max_tasks + 127) / 128), 128, 0, st>>>(
+            reinterpret_cast<const affine_t<F>*>(d_bases), entries, offsets, task_off, task_bucket, nb, buckets, task_sums);
     }
     B2_TRY(check_launch(ctx, "k_msm_accumulate"));
     {
+        LaunchScope ls(ctx, st, "msm_merge");
+        k_msm_merge_tasks<F><<<2 * ctx->sm_count, 128, 0, st>>>(multi + 1, multi, task_off, task_sums, buckets);
+    }
+    B2_TRY(check_launch(ctx, "k_msm_merge_tasks"));
+    {
         LaunchScope ls(ctx, st, "msm_reduce");
-        k_msm_reduce_segments<F><<<(W * nseg + 127) / 128, 128, 0, st>>>(buckets, W, B, seg_len, partials);
+        k_msm_reduce_segments<F><<<(4 * W * nseg + 127) / 128, 128, 0, st>>>(buckets, W, B, seg_len, partials);
     }
     B2_TRY(check_launch(ctx, "k_msm_reduce_segments"));
     {
         LaunchScope ls(ctx, st, "msm_reduce");
-        constexpr int T = sizeof(F) > 32 ? 128 : 256;
+        constexpr int T = 256;
         k_msm_window_sum<F, T><<<W, T, 0, st>>>(partials, nseg, wsum);
     }
     B2_TRY(check_launch(ctx, "k_msm_window_sum"));
     {
         LaunchScope ls(ctx, st, "msm_combine");
-        k_msm_combine<F><<<1, 32, 0, st>>>(wsum, W, c, out);
+        k_msm_combine<F><<<1, 4, 0, st>>>(wsum, W, c, out);
     }
     return check_launch(ctx, "k_msm_combine");
 }
