@@ -52,6 +52,10 @@ SIGNATURES = {
                                          ctypes.c_uint]),
     "b200zk_ntt_fr_fourstep_cols_dev": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_uint, ctypes.c_uint,
                                                        ctypes.c_uint, ctypes.c_uint64, ctypes.c_int]),
+    "b200zk_ntt_fr_batched_post_dev": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_uint, ctypes.c_uint,
+                                                      ctypes.c_int, ctypes.c_uint, ctypes.c_int, ctypes.c_uint64,
+                                                      ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64]),
+    "b200zk_fr_mul_sub_dev": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t]),
     "b200zk_h_circom": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_uint, c_vp]),
     "b200zk_h_circom_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_uint, c_vp]),
     "b200zk_pk_upload": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t, ctypes.c_size_t,

@@ -250,6 +250,23 @@ int b200zk_ntt_fr_fourstep_cols_dev(b200zk_ctx* ctx, int stream, const void* d_i
                              log_cols_local, log_n, global_col0, inverse != 0);
 }
 
+int b200zk_ntt_fr_batched_post_dev(b200zk_ctx* ctx, int stream, const void* d_in, void* d_out, unsigned log_t, unsigned batch,
+                                   int inverse, unsigned log_base, int base_is_shift, uint64_t b0, uint64_t alpha,
+                                   uint64_t beta, uint64_t gamma) {
+    if (!ctx || !valid_slot(stream) || !d_in || !d_out || batch == 0) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[stream];
+    std::lock_guard<std::mutex> g(sl.mu);
+    return ntt_batched_post_dev(ctx, sl, reinterpret_cast<const Fr*>(d_in), reinterpret_cast<Fr*>(d_out), log_t, batch,
+                                inverse != 0, log_base, base_is_shift != 0, b0, alpha, beta, gamma);
+}
+
+int b200zk_fr_mul_sub_dev(b200zk_ctx* ctx, int stream, const void* d_a, const void* d_b, const void* d_c, void* d_out, size_t n) {
+    if (!ctx || !valid_slot(stream) || (n && (!d_a || !d_b || !d_c || !d_out))) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[stream];
+    std::lock_guard<std::mutex> g(sl.mu);
+    return mul_sub_dev(ctx, sl, (const Fr*)d_a, (const Fr*)d_b, (const Fr*)d_c, (Fr*)d_out, n);
+}
+
 // ---- h -----------------------------------------------------------------------------------------
 int b200zk_h_circom_dev(b200zk_ctx* ctx, const void* d_a, const void* d_b, const void* d_c, unsigned log_m, void* d_h) {
     if (!ctx || !d_a || !d_b || !d_c || !d_h) return B200ZK_ERR_ARG;

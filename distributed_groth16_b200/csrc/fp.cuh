@@ -29,7 +29,7 @@
 
 // build-time experiment switches (tools/variants.sh): multiplier schedule and inlining
 #ifndef B2_MUL_VARIANT
-#define B2_MUL_VARIANT 1      // 0: mad.lo.cc/madc.hi.cc rows everywhere; 1: IMAD.WIDE + IADD3 chains for the a*b rows
+#define B2_MUL_VARIANT 0      // 0: mad.lo.cc/madc.hi.cc rows everywhere; 1: IMAD.WIDE + IADD3 chains for the a*b rows
 #endif
 #ifndef B2_MUL_NOINLINE
 #define B2_MUL_NOINLINE 0     // 1: Fp::mul is an out-of-line call (small I-cache footprint)

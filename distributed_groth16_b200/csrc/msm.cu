@@ -181,12 +181,50 @@ __global__ void k_msm_fill_tasks(const uint32_t* task_off, uint32_t nbuckets, ui
     if (hi - lo > 1) multi_list[atomicAdd(multi_count, 1u)] = g;
 }
 
-template <class F>
-__global__ void __launch_bounds__(128, B2_ACC_MINBLOCKS) k_msm_accumulate(const affine_t<F>* bases, const uint32_t* entries, const uint32_t* offsets,
-                                 const uint32_t* task_off, const uint32_t* task_bucket, uint32_t nbuckets,
-                                 xyzz_t<F>* buckets, xyzz_t<F>* task_sums) {
+// Counting sort of the tasks by length (descending): the lanes of a warp then run loops of (almost)
+// equal length.  Unsorted, bucket sizes ~Poisson(32) leave only 23 of 32 lanes active on average
+// (ncu smsp__thread_inst_executed_per_inst_executed, profiles/r1a_full.md).
+__device__ __forceinline__ uint32_t task_length(const uint32_t* offsets, const uint32_t* task_off, uint32_t g, uint32_t t) {
+    uint32_t lo = offsets[g] + (t - task_off[g]) * TASK_LEN, end = offsets[g + 1];
+    return (lo + TASK_LEN < end ? lo + TASK_LEN : end) - lo;
+}
+__global__ void __launch_bounds__(256) k_msm_task_hist(const uint32_t* offsets, const uint32_t* task_off, const uint32_t* task_bucket,
+                                uint32_t nbuckets, uint32_t* hist, uint32_t* task_rank) {
+    __shared__ uint32_t sh_cnt[TASK_LEN + 1], sh_base[TASK_LEN + 1];     // block-local histogram first:
+    for (uint32_t i = threadIdx.x; i <= TASK_LEN; i += blockDim.x) sh_cnt[i] = 0;   // few hot bins -> keep contention in smem
+    __syncthreads();
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = t < task_off[nbuckets];
+    uint32_t len = 0, local = 0;
+    if (live) {
+        len = task_length(offsets, task_off, task_bucket[t], t);
+        local = atomicAdd(sh_cnt + len, 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i <= TASK_LEN; i += blockDim.x)
+        if (sh_cnt[i]) sh_base[i] = atomicAdd(hist + i, sh_cnt[i]);
+    __syncthreads();
+    if (live) task_rank[t] = sh_base[len] + local;
+}
+__global__ void k_msm_task_hist_scan(uint32_t* hist) {      // base[len] = #tasks longer than len; 1 thread
+    uint32_t run = 0;
+    for (int len = (int)TASK_LEN; len >= 0; --len) { uint32_t c = hist[len]; hist[len] = run; run += c; }
+}
+__global__ void k_msm_task_order(const uint32_t* offsets, const uint32_t* task_off, const uint32_t* task_bucket,
+                                 uint32_t nbuckets, const uint32_t* hist, const uint32_t* task_rank, uint32_t* order) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= task_off[nbuckets]) return;
+    uint32_t len = task_length(offsets, task_off, task_bucket[t], t);
+    order[hist[len] + task_rank[t]] = t;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128, B2_ACC_MINBLOCKS) k_msm_accumulate(const affine_t<F>* bases, const uint32_t* entries, const uint32_t* offsets,
+                                 const uint32_t* task_off, const uint32_t* task_bucket, const uint32_t* order,
+                                 uint32_t nbuckets, xyzz_t<F>* buckets, xyzz_t<F>* task_sums) {
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= task_off[nbuckets]) return;
+    uint32_t t = order[tid];
     uint32_t g = task_bucket[t];
     uint32_t t0 = task_off[g], nt = task_off[g + 1] - t0;
     uint32_t lo = offsets[g] + (t - t0) * TASK_LEN, end = offsets[g + 1];
@@ -233,31 +271,31 @@ __global__ void __launch_bounds__(128) k_msm_merge_tasks(const uint32_t* multi_l
 // ---------------------------------------------------------------------------------------------
 // 5. window reduction: S_w = sum_{k<B} (k+1) * bucket[w][k]
 // ---------------------------------------------------------------------------------------------
-// one quad (4 lanes, quad_ops) per (window, segment)
+// one thread per (window, segment).  (A quad-cooperative version of this kernel was measured slower,
+// 1.52 ms vs 0.79 ms at 2^20: it is throughput- not latency-bound.)
 template <class F>
 __global__ void __launch_bounds__(128) k_msm_reduce_segments(const xyzz_t<F>* buckets, uint32_t W, uint32_t B, uint32_t seg_len,
                                       xyzz_t<F>* partials) {
-    typedef quad_ops<F> Q;
     uint32_t nseg = B / seg_len;
-    uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= W * nseg) return;
     uint32_t w = t / nseg, seg = t % nseg;
     uint32_t lo = seg * seg_len;
     const xyzz_t<F>* bw = buckets + (size_t)w * B;
     xyzz_t<F> run = xyzz_t<F>::identity(), acc = xyzz_t<F>::identity();
     for (uint32_t k = lo + seg_len; k-- > lo;) {
-        run = Q::add(run, ld16(bw + k));
-        acc = Q::add(acc, run);
+        run = xyzz_t<F>::add(run, ld16(bw + k));
+        acc = xyzz_t<F>::add(acc, run);
     }
     if (lo) {   // + lo * run
         xyzz_t<F> m = xyzz_t<F>::identity();
         for (int bit = 31 - __clz(lo); bit >= 0; --bit) {
-            m = Q::dbl(m);
-            if ((lo >> bit) & 1) m = Q::add(m, run);
+            m = xyzz_t<F>::dbl(m);
+            if ((lo >> bit) & 1) m = xyzz_t<F>::add(m, run);
         }
-        acc = Q::add(acc, m);
+        acc = xyzz_t<F>::add(acc, m);
     }
-    if ((threadIdx.x & 3) == 0) st16(partials + t, acc);
+    st16(partials + t, acc);
 }
 
 // one block per window: sum nseg partials (THREADS / 4 quads)
@@ -375,7 +413,10 @@ static int msm_dev_impl(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const vo
     size_t o_taskoff = o_ntasks + al(((size_t)nb + 1) * 4);
     size_t o_taskbucket = o_taskoff + al(((size_t)nb + 1) * 4);
     size_t o_multi = o_taskbucket + al(max_tasks * 4);
-    size_t o_tasksums = o_multi + al((total / TASK_LEN + 2) * 4);
+    size_t o_hist = o_multi + al((total / TASK_LEN + 2) * 4);
+    size_t o_rank = o_hist + al((TASK_LEN + 1) * 4);
+    size_t o_order = o_rank + al(max_tasks * 4);
+    size_t o_tasksums = o_order + al(max_tasks * 4);
     size_t o_buckets = o_tasksums + al(max_tasks * sizeof(xyzz_t<F>));
     size_t o_partials = o_buckets + al((size_t)nb * sizeof(xyzz_t<F>));
     size_t o_wsum = o_partials + al((size_t)W * nseg * sizeof(xyzz_t<F>));
@@ -392,6 +433,9 @@ static int msm_dev_impl(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const vo
     uint32_t* task_off = reinterpret_cast<uint32_t*>(ws + o_taskoff);
     uint32_t* task_bucket = reinterpret_cast<uint32_t*>(ws + o_taskbucket);
     uint32_t* multi = reinterpret_cast<uint32_t*>(ws + o_multi);       // [0] = count, [1..] = list
+    uint32_t* hist = reinterpret_cast<uint32_t*>(ws + o_hist);
+    uint32_t* task_rank = reinterpret_cast<uint32_t*>(ws + o_rank);
+    uint32_t* order = reinterpret_cast<uint32_t*>(ws + o_order);
     xyzz_t<F>* task_sums = reinterpret_cast<xyzz_t<F>*>(ws + o_tasksums);
     xyzz_t<F>* buckets = reinterpret_cast<xyzz_t<F>*>(ws + o_buckets);
     xyzz_t<F>* partials = reinterpret_cast<xyzz_t<F>*>(ws + o_partials);
@@ -418,6 +462,20 @@ static int msm_dev_impl(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const vo
         k_msm_fill_tasks<<<(nb + 255) / 256, 256, 0, st>>>(task_off, nb, task_bucket, multi + 1, multi);
     }
     B2_TRY(check_launch(ctx, "k_msm_fill_tasks"));
+    B2_CUDA_OK(ctx, cudaMemsetAsync(hist, 0, (TASK_LEN + 1) * 4, st));
+    {
+        LaunchScope ls(ctx, st, "msm_tasks");
+        k_msm_task_hist<<<(unsigned)((max_tasks + 255) / 256), 256, 0, st>>>(offsets, task_off, task_bucket, nb, hist, task_rank);
+    }
+    {
+        LaunchScope ls(ctx, st, "msm_tasks");
+        k_msm_task_hist_scan<<<1, 1, 0, st>>>(hist);
+    }
+    {
+        LaunchScope ls(ctx, st, "msm_tasks");
+        k_msm_task_order<<<(unsigned)((max_tasks + 255) / 256), 256, 0, st>>>(offsets, task_off, task_bucket, nb, hist, task_rank, order);
+    }
+    B2_TRY(check_launch(ctx, "k_msm_task_order"));
     {
         LaunchScope ls(ctx, st, "msm_scatter");
         k_msm_scatter<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(keys, ranks, offsets, (uint32_t)n, total, entries);
@@ -426,7 +484,7 @@ static int msm_dev_impl(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const vo
     {
         LaunchScope ls(ctx, st, acc_name);
         k_msm_accumulate<F><<<(unsigned)((max_tasks + 127) / 128), 128, 0, st>>>(
-            reinterpret_cast<const affine_t<F>*>(d_bases), entries, offsets, task_off, task_bucket, nb, buckets, task_sums);
+            reinterpret_cast<const affine_t<F>*>(d_bases), entries, offsets, task_off, task_bucket, order, nb, buckets, task_sums);
     }
     B2_TRY(check_launch(ctx, "k_msm_accumulate"));
     {
@@ -436,11 +494,11 @@ static int msm_dev_impl(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const vo
     B2_TRY(check_launch(ctx, "k_msm_merge_tasks"));
     {
         LaunchScope ls(ctx, st, "msm_reduce");
-        k_msm_reduce_segments<F><<<(4 * W * nseg + 127) / 128, 128, 0, st>>>(buckets, W, B, seg_len, partials);
+        k_msm_reduce_segments<F><<<(W * nseg + 127) / 128, 128, 0, st>>>(buckets, W, B, seg_len, partials);
     }
     B2_TRY(check_launch(ctx, "k_msm_reduce_segments"));
     {
-        LaunchScope ls(ctx, st, "msm_reduce");
+        LaunchScope ls(ctx, st, "msm_window_sum");
         constexpr int T = 256;
         k_msm_window_sum<F, T><<<W, T, 0, st>>>(partials, nseg, wsum);
     }

@@ -113,6 +113,10 @@ struct PassParams {
     PowTab post;
     const Fr* post_const;
     int apply_tw, apply_pre, apply_post, apply_post_const;
+    // post exponent = (batch + post_b0) * (post_alpha * k + post_beta) + post_gamma * k   (k = output index);
+    // the single-GPU transforms use (alpha, beta, gamma) = (0, 0, 1); the four-step column twiddle
+    // w_N^(col * k1) uses (1, 0, 0) and the distributed coefficient shift w_2m^(k1 + N1 k2) uses (0, 1, N1).
+    uint64_t post_b0, post_alpha, post_beta, post_gamma;
     size_t batch_stride;
 };
 
@@ -186,7 +190,10 @@ __global__ void __launch_bounds__(512) k_ntt_pass(PassParams p) {
             if (ex) v = Fr::mul(v, powtab_get(p.tw, ex));
         }
         uint64_t oaddr = ((j + ((uint64_t)ks << p.logL)) << p.logM) + n2;
-        if (p.apply_post) v = Fr::mul(v, powtab_get(p.post, oaddr));
+        if (p.apply_post) {
+            uint64_t ex = (blockIdx.y + p.post_b0) * (p.post_alpha * oaddr + p.post_beta) + p.post_gamma * oaddr;
+            if (ex) v = Fr::mul(v, powtab_get(p.post, ex));
+        }
         if (p.apply_post_const) v = Fr::mul(v, ld_fr(p.post_const));
         st_fr(out + oaddr, v);
     }
@@ -282,8 +289,11 @@ void ntt_free_plans(b200zk_ctx* ctx) {
 }
 
 // Runs all passes.  pre / post may be null.  post_const: device pointer or null.
+struct PostExp { uint64_t b0, alpha, beta, gamma; };
+static const PostExp POST_PLAIN = {0, 0, 0, 1};
+
 static int ntt_run(b200zk_ctx* ctx, Slot& sl, NttPlan* pl, const Fr* d_in, Fr* d_out, unsigned batch,
-                   const PowTab* pre, const PowTab* post, const Fr* post_const) {
+                   const PowTab* pre, const PowTab* post, const Fr* post_const, PostExp pe = POST_PLAIN) {
     cudaStream_t st = sl.stream;
     const size_t N = (size_t)1 << pl->log_n;
     if (pl->npass == 0) {   // N == 1: X[0] = x[0] (all scale factors are 1)
@@ -311,7 +321,10 @@ static int ntt_run(b200zk_ctx* ctx, Slot& sl, NttPlan* pl, const Fr* d_in, Fr* d
         p.tw = pl->tw;
         p.apply_tw = last ? 0 : 1;
         if (i == 0 && pre) { p.pre = *pre; p.apply_pre = 1; }
-        if (last && post) { p.post = *post; p.apply_post = 1; }
+        if (last && post) {
+            p.post = *post; p.apply_post = 1;
+            p.post_b0 = pe.b0; p.post_alpha = pe.alpha; p.post_beta = pe.beta; p.post_gamma = pe.gamma;
+        }
         if (last && post_const) { p.post_const = post_const; p.apply_post_const = 1; }
         p.batch_stride = N;
         uint32_t RG = 1u << (p.logR + p.logG);
@@ -381,8 +394,44 @@ int h_circom_dev(b200zk_ctx* ctx, Slot& sl, const Fr* d_a, const Fr* d_b, const 
     return check_launch(ctx, "k_h_pointwise");
 }
 
-int fourstep_cols_dev(b200zk_ctx* ctx, Slot&, const Fr*, Fr*, unsigned, unsigned, unsigned, uint64_t, bool) {
-    return set_error(ctx, B200ZK_ERR_ARG, "four-step column transform: not built yet");
+// Batched transform of size 2^log_t over `batch` contiguous vectors with a per-batch post factor
+// base^((b + b0)(alpha k + beta) + gamma k), base = w_{2^log_base} (forward root, or its inverse when
+// `inverse`); the inverse transform also scales by 2^-log_t.  Building block of the multi-GPU four-step
+// NTT and of the distributed h pipeline (dist_primitives/dfft_sharded.py).
+int ntt_batched_post_dev(b200zk_ctx* ctx, Slot& sl, const Fr* d_in, Fr* d_out, unsigned log_t, unsigned batch, bool inverse,
+                         unsigned log_base, bool base_is_shift, uint64_t b0, uint64_t alpha, uint64_t beta, uint64_t gamma) {
+    if (log_t > 28 || log_base > 28 || log_t == 0) return set_error(ctx, B200ZK_ERR_DOMAIN, "bad transform size for batched NTT");
+    NttPlan *pl, *base_plan;
+    B2_TRY(get_plan(ctx, sl.stream, log_t, inverse, &pl));
+    const PowTab* tab = nullptr;
+    if (base_is_shift) {
+        // powers of the FORWARD root w_{2^(log_base)} = consts[3] of the (log_base - 1) plan
+        B2_TRY(get_plan(ctx, sl.stream, log_base - 1, true, &base_plan));
+        PowTab* t;
+        B2_TRY(plan_lazy_tab(ctx, sl.stream, base_plan, 3, &t));
+        tab = t;
+        // the shift table covers exponents < 2^(log_base-1); callers keep (k1 + N1 k2) < m = 2^(log_base-1)
+    } else {
+        B2_TRY(get_plan(ctx, sl.stream, log_base, inverse, &base_plan));
+        tab = &base_plan->tw;
+    }
+    PostExp pe = {b0, alpha, beta, gamma};
+    return ntt_run(ctx, sl, pl, d_in, d_out, batch, nullptr, tab, inverse ? pl->consts + 1 : nullptr, pe);
+}
+
+int fourstep_cols_dev(b200zk_ctx* ctx, Slot& sl, const Fr* d_in, Fr* d_out, unsigned log_rows, unsigned log_cols_local,
+                      unsigned log_n, uint64_t global_col0, bool inverse) {
+    return ntt_batched_post_dev(ctx, sl, d_in, d_out, log_rows, 1u << log_cols_local, inverse, log_n, false, global_col0, 1, 0, 0);
+}
+
+// out[i] = a[i]*b[i] - c[i]   (ext_wit.rs:88-92 on device-resident vectors)
+int mul_sub_dev(b200zk_ctx* ctx, Slot& sl, const Fr* a, const Fr* b, const Fr* c, Fr* out, size_t n) {
+    if (n == 0) return B200ZK_OK;
+    {
+        LaunchScope ls(ctx, sl.stream, "h_pointwise");
+        k_h_pointwise<<<(unsigned)((n + 255) / 256), 256, 0, sl.stream>>>(a, b, c, out, n);
+    }
+    return check_launch(ctx, "k_h_pointwise");
 }
 
 }  // namespace b200zk

@@ -92,6 +92,17 @@ int b200zk_ntt_fr_dev(b200zk_ctx* ctx, int stream, const void* d_in, void* d_out
 int b200zk_ntt_fr_fourstep_cols_dev(b200zk_ctx* ctx, int stream, const void* d_in, void* d_out, unsigned log_rows,
                                     unsigned log_cols_local, unsigned log_n, uint64_t global_col0, int inverse);
 
+/* Generalised building block: `batch` contiguous transforms of size 2^log_t; output k of transform b is
+ * multiplied by base^((b + b0)(alpha k + beta) + gamma k) where base = w_{2^log_base} (direction of the
+ * transform) or, with base_is_shift, the forward root w_{2^log_base} used by the h coefficient shift.
+ * fourstep_cols == (b0 = global_col0, alpha = 1, beta = 0, gamma = 0, log_base = log_n). */
+int b200zk_ntt_fr_batched_post_dev(b200zk_ctx* ctx, int stream, const void* d_in, void* d_out, unsigned log_t,
+                                   unsigned batch, int inverse, unsigned log_base, int base_is_shift, uint64_t b0,
+                                   uint64_t alpha, uint64_t beta, uint64_t gamma);
+/* out[i] = a[i]*b[i] - c[i] on device-resident vectors (the king's pointwise step, ext_wit.rs:88-92). */
+int b200zk_fr_mul_sub_dev(b200zk_ctx* ctx, int stream, const void* d_a, const void* d_b, const void* d_c, void* d_out,
+                          size_t n);
+
 /* ---- ext_wit::h (groth16/src/ext_wit.rs:16-101 == ark-circom/src/circom/qap.rs:64-89) --------- */
 /* a, b, c: QAP evaluation vectors (2^log_m x 4 limbs each); h_out[i] = A(w^(2i+1)) B(..) - C(..). */
 int b200zk_h_circom(b200zk_ctx* ctx, const uint64_t* a, const uint64_t* b, const uint64_t* c, unsigned log_m,

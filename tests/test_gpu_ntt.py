@@ -85,3 +85,12 @@ def test_linearity_2_20(net, cref):
     fa, fb = net.ntt(ah), net.ntt(bh)
     assert (net.field_op(1, 1, fa, fb) == fs).all()
     assert (fa == cref.ntt(ah)).all()
+
+
+def test_config3_2_22_vs_oracle(net, cref):
+    """BASELINE config 3: 2^22 elements, forward, inverse and coset variants against the CPU twin."""
+    n = 1 << 22
+    x = net.generate_fr(0xB2000003, n).cpu().numpy().view(np.uint64)
+    assert (net.ntt(x) == cref.ntt(x)).all()
+    assert (net.ntt(x, inverse=True) == cref.ntt(x, inverse=True)).all()
+    assert (net.ntt(x, coset=True) == cref.ntt(x, coset=True)).all()

@@ -74,3 +74,43 @@ def test_prove_structs_mirror_reference_call_pattern(net, cref):
     from oracle import bn254 as o
     got = o.proof_compress(layout.arr_to_g1(A2)[0], layout.arr_to_g2(B2)[0], layout.arr_to_g1(C.limbs)[0])
     assert got == exp
+
+
+def test_f1_real_zkey_prove_on_gpu_matches_golden_and_verifies(net):
+    """Fixture F1: proving key of the snarkjs-made complex-circuit-10000-10000.zkey, witness a = 3.
+    The GPU proof must equal the committed golden bytes (oracle-produced, pairing-verified against the zkey's vk)
+    for r = s = 0 and for r, s != 0; the r = s = 0 proof is verified again here."""
+    import json
+    import os
+    from oracle import bn254 as o, layout
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    d = np.load(os.path.join(G, "complex_circuit.zkey.pk.npz"))
+    exp = json.load(open(os.path.join(G, "complex_circuit_proof.json")))
+    n_vars, n_public, m, nc = (int(x) for x in d["dims"])
+    z = [0] * n_vars
+    z[0], z[2] = 1, 3
+    for i in range(3, n_vars):
+        z[i] = z[i - 1] * z[i - 1] % o.R
+    z[1] = z[n_vars - 1] ** 2 % o.R
+    # QAP rows of this chain circuit: A_i = -w_{i+2}, B_i = w_{i+2} (read from the zkey's coefficient section)
+    vals_a, vals_b = layout.arr_to_fr(d["a_vals"]), layout.arr_to_fr(d["b_vals"])
+    a = [0] * m
+    b = [0] * m
+    for r_, c_, v in zip(d["a_rows"], d["a_cols"], vals_a):
+        a[int(r_)] = (a[int(r_)] + v * z[int(c_)]) % o.R
+    for r_, c_, v in zip(d["b_rows"], d["b_cols"], vals_b):
+        b[int(r_)] = (b[int(r_)] + v * z[int(c_)]) % o.R
+    for j in range(n_public + 1):
+        a[nc + j] = z[j]
+    c = [x * y % o.R for x, y in zip(a, b)]
+    pk = ProvingKey(net, d["a_query"], d["b_g1_query"], d["b_g2_query"], d["l_query"], d["h_query"], n_public + 1,
+                    d["vk_g1"][0], d["vk_g1"][1], d["vk_g1"][2], d["vk_g2"][0], d["vk_g2"][1])
+    zz, aa, bb, cc = (layout.fr_to_arr(v) for v in (z, a, b, c))
+    for key in ("r0s0", "r_s"):
+        r, s = layout.fr_to_arr([exp[key]["r"]])[0], layout.fr_to_arr([exp[key]["s"]])[0]
+        got = prove.create_proof(pk, zz, aa, bb, cc, r, s)
+        assert got.hex() == exp[key]["proof_hex"], key
+    A, B, C = o.proof_decompress(prove.create_proof(pk, zz, aa, bb, cc))
+    vk1, vk2 = layout.arr_to_g1(d["vk_g1"]), layout.arr_to_g2(d["vk_g2"])
+    assert o.groth16_verify(vk1[0], vk2[0], vk2[2], vk2[1], layout.arr_to_g1(d["ic"]), [z[1]], A, B, C)
+    pk.free()
