@@ -51,8 +51,11 @@ struct xyzz_t {
         return r;
     }
 
+    B2_HD_NI static xyzz_t dbl(const xyzz_t& p) { return dbl_inl(p); }
+    B2_HD_NI static xyzz_t add(const xyzz_t& a, const xyzz_t& b) { return add_inl(a, b); }
+
     // dbl-2008-s-1
-    B2_HD_NI static xyzz_t dbl(const xyzz_t& p) {
+    B2_HD static xyzz_t dbl_inl(const xyzz_t& p) {
         if (p.is_inf()) return p;
         F U = F::dbl(p.y);
         F V = F::sqr(U);
@@ -97,7 +100,7 @@ struct xyzz_t {
     }
 
     // add-2008-s
-    B2_HD_NI static xyzz_t add(const xyzz_t& a, const xyzz_t& b) {
+    B2_HD static xyzz_t add_inl(const xyzz_t& a, const xyzz_t& b) {
         if (a.is_inf()) return b;
         if (b.is_inf()) return a;
         F U1 = F::mul(a.x, b.zz);
@@ -107,7 +110,7 @@ struct xyzz_t {
         F Pp = F::sub(U2, U1);
         F R = F::sub(S2, S1);
         if (Pp.is_zero()) {
-            if (R.is_zero()) return dbl(a);
+            if (R.is_zero()) return dbl(a);      // rare: out-of-line
             return identity();
         }
         F PP = F::sqr(Pp);
@@ -156,11 +159,14 @@ struct xyzz_t {
 // results are exchanged with quad-wide shuffles: an XYZZ addition becomes 4 product-latencies instead
 // of 14, a doubling 3 instead of 9.  All lanes of a quad must call with identical arguments.
 // ---------------------------------------------------------------------------------------------
-template <class F>
+// FULLWARP = true: every lane of the warp executes the same call sequence (e.g. one warp doing one chain
+// redundantly in its 8 quads), so the shuffles can use the full mask -- with a runtime quad mask the compiler
+// wraps every SHFL in a WARPSYNC/collective sequence, which more than doubles the latency of an operation.
+template <class F, bool FULLWARP = false>
 struct quad_ops {
     static constexpr int WORDS = sizeof(F) / 4;
 
-    __device__ __forceinline__ static unsigned quad_mask() { return 0xFu << (threadIdx.x & 28u); }
+    __device__ __forceinline__ static unsigned quad_mask() { return FULLWARP ? 0xFFFFFFFFu : (0xFu << (threadIdx.x & 28u)); }
     __device__ __forceinline__ static int quad_lane() { return threadIdx.x & 3; }
 
     __device__ __forceinline__ static F bcast(const F& v, int src) {

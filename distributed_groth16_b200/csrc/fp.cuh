@@ -256,8 +256,8 @@ struct Fp {
         Fp o = zero(); o.l[0] = 1;
         return mul(a, o);
     }
-    // a^(p-2) (Fermat); only used for the handful of affine normalisations per call
-    B2_HD_NI static Fp inv(const Fp& a) {
+    // a^(p-2) (Fermat) -- kept as the slow cross-check of inv()
+    B2_HD_NI static Fp inv_fermat(const Fp& a) {
         Fp res = one();
         for (int i = 255; i >= 0; --i) {
             res = mul_ni(res, res);
@@ -267,6 +267,75 @@ struct Fp {
             if ((w >> (i & 31)) & 1) res = mul_ni(res, a);
         }
         return res;
+    }
+
+    // Montgomery inverse by the binary extended Euclid ("almost inverse", Kaliski): ~2*254 shift/subtract
+    // steps on 256-bit integers instead of ~380 dependent field multiplications -- the affine normalisation
+    // is a single-thread latency chain at the end of every MSM (0.28 ms -> ~0.03 ms per call).
+    // Input/outputs in Montgomery form; inv(0) = 0.
+    B2_HD_NI static Fp inv(const Fp& a) {
+        if (a.is_zero()) return a;
+        uint32_t u[8], v[8], r[8], s[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { u[i] = P::mod(i); v[i] = a.l[i]; r[i] = 0; s[i] = 0; }
+        s[0] = 1;
+        int k = 0;
+        for (;;) {
+            uint32_t vz = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vz |= v[i];
+            if (vz == 0) break;
+            if ((u[0] & 1) == 0) { shr1(u); shl1(s); }
+            else if ((v[0] & 1) == 0) { shr1(v); shl1(r); }
+            else if (gt(u, v)) { sub_n(u, v); shr1(u); add_n(r, s); shl1(s); }
+            else { sub_n(v, u); shr1(v); add_n(s, r); shl1(r); }
+            ++k;
+        }
+        // r < 2p; r = p - (r mod p) = (aR)^-1 * 2^k
+        Fp t;
+        final_sub(t, r);
+        t = neg(t);
+        // t*R^2*R^-1 = a^-1 * 2^k, then * 2^(512-k) * R^-1 = a^-1 * R
+        t = mul_ni(t, r2());
+        int j = 512 - k;                         // k in [254, 508]
+        if (j >= 256) {
+            for (int d = 0; d < j - 256; ++d) t = dbl(t);
+            return t;
+        }
+        Fp pw = zero();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if ((j >> 5) == i) pw.l[i] = 1u << (j & 31);
+        return mul_ni(t, pw);                    // second operand may exceed p: only the rows use it (see mul)
+    }
+    B2_HD static void shr1(uint32_t* x) {
+#pragma unroll
+        for (int i = 0; i < 7; ++i) x[i] = (x[i] >> 1) | (x[i + 1] << 31);
+        x[7] >>= 1;
+    }
+    B2_HD static void shl1(uint32_t* x) {
+#pragma unroll
+        for (int i = 7; i > 0; --i) x[i] = (x[i] << 1) | (x[i - 1] >> 31);
+        x[0] <<= 1;
+    }
+    B2_HD static bool gt(const uint32_t* x, const uint32_t* y) {
+#pragma unroll
+        for (int i = 7; i >= 0; --i) {
+            if (x[i] > y[i]) return true;
+            if (x[i] < y[i]) return false;
+        }
+        return false;
+    }
+    B2_HD static void sub_n(uint32_t* x, const uint32_t* y) {          // x -= y (x >= y)
+        x[0] = cc::sub_cc(x[0], y[0]);
+#pragma unroll
+        for (int i = 1; i < 7; ++i) x[i] = cc::subc_cc(x[i], y[i]);
+        x[7] = cc::subc(x[7], y[7]);
+    }
+    B2_HD static void add_n(uint32_t* x, const uint32_t* y) {          // x += y (no overflow: < 2^256)
+        x[0] = cc::add_cc(x[0], y[0]);
+#pragma unroll
+        for (int i = 1; i < 7; ++i) x[i] = cc::addc_cc(x[i], y[i]);
+        x[7] = cc::addc(x[7], y[7]);
     }
     B2_HD static Fp from_u32(uint32_t v) { Fp o = zero(); o.l[0] = v; return to_mont(o); }
 };

@@ -239,27 +239,29 @@ __global__ void __launch_bounds__(128, B2_ACC_MINBLOCKS) k_msm_accumulate(const 
     else st16(task_sums + t, acc);
 }
 
-// buckets[g] = sum of the task sums of g, for every multi-task bucket; one block (32 quads) per bucket, grid-strided
+template <class F>
+__device__ __forceinline__ xyzz_t<F> add_sel(const xyzz_t<F>& a, const xyzz_t<F>& b) {
+    if (sizeof(F) == 32) return xyzz_t<F>::add_inl(a, b);      // G1: inline (see k_msm_reduce_segments)
+    return xyzz_t<F>::add(a, b);
+}
+
+// buckets[g] = sum of the task sums of g, for every multi-task bucket; one block per bucket, grid-strided
 template <class F>
 __global__ void __launch_bounds__(128) k_msm_merge_tasks(const uint32_t* multi_list, const uint32_t* multi_count,
                                   const uint32_t* task_off, const xyzz_t<F>* task_sums, xyzz_t<F>* buckets) {
-    typedef quad_ops<F> Q;
-    __shared__ xyzz_t<F> sh[32];
-    const uint32_t qid = threadIdx.x >> 2, ql = threadIdx.x & 3;
+    __shared__ xyzz_t<F> sh[128];
     uint32_t cnt = *multi_count;
     for (uint32_t i = blockIdx.x; i < cnt; i += gridDim.x) {
         uint32_t g = multi_list[i];
         uint32_t lo = task_off[g], hi = task_off[g + 1];
         xyzz_t<F> acc = xyzz_t<F>::identity();
-        for (uint32_t t = lo + qid; t < hi; t += 32) acc = Q::add(acc, ld16(task_sums + t));
-        if (ql == 0) sh[qid] = acc;
+        for (uint32_t t = lo + threadIdx.x; t < hi; t += 128) acc = add_sel<F>(acc, ld16(task_sums + t));
+        sh[threadIdx.x] = acc;
         __syncthreads();
-        for (int s = 16; s > 0; s >>= 1) {
-            if ((int)qid < s) {
-                xyzz_t<F> a = sh[qid], b = sh[qid + s];
-                a = Q::add(a, b);
-                __syncwarp(Q::quad_mask());
-                if (ql == 0) sh[qid] = a;
+        for (int s = 64; s > 0; s >>= 1) {
+            if ((int)threadIdx.x < s) {
+                xyzz_t<F> a = sh[threadIdx.x], b = sh[threadIdx.x + s];
+                sh[threadIdx.x] = add_sel<F>(a, b);
             }
             __syncthreads();
         }
@@ -283,50 +285,50 @@ __global__ void __launch_bounds__(128) k_msm_reduce_segments(const xyzz_t<F>* bu
     uint32_t lo = seg * seg_len;
     const xyzz_t<F>* bw = buckets + (size_t)w * B;
     xyzz_t<F> run = xyzz_t<F>::identity(), acc = xyzz_t<F>::identity();
+    // G1: the group law is inlined here (an out-of-line call moves 3 x 128 B through local memory per
+    // operation, which dominated this latency-bound chain); G2 keeps the calls to bound code size.
+    constexpr bool INL = sizeof(F) == 32;
     for (uint32_t k = lo + seg_len; k-- > lo;) {
-        run = xyzz_t<F>::add(run, ld16(bw + k));
-        acc = xyzz_t<F>::add(acc, run);
+        xyzz_t<F> bk = ld16(bw + k);
+        if (INL) { run = xyzz_t<F>::add_inl(run, bk); acc = xyzz_t<F>::add_inl(acc, run); }
+        else { run = xyzz_t<F>::add(run, bk); acc = xyzz_t<F>::add(acc, run); }
     }
     if (lo) {   // + lo * run
         xyzz_t<F> m = xyzz_t<F>::identity();
         for (int bit = 31 - __clz(lo); bit >= 0; --bit) {
-            m = xyzz_t<F>::dbl(m);
-            if ((lo >> bit) & 1) m = xyzz_t<F>::add(m, run);
+            if (INL) m = xyzz_t<F>::dbl_inl(m); else m = xyzz_t<F>::dbl(m);
+            if ((lo >> bit) & 1) { if (INL) m = xyzz_t<F>::add_inl(m, run); else m = xyzz_t<F>::add(m, run); }
         }
-        acc = xyzz_t<F>::add(acc, m);
+        if (INL) acc = xyzz_t<F>::add_inl(acc, m); else acc = xyzz_t<F>::add(acc, m);
     }
     st16(partials + t, acc);
 }
 
-// one block per window: sum nseg partials (THREADS / 4 quads)
+// one block per window: sum nseg partials
 template <class F, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_msm_window_sum(const xyzz_t<F>* partials, uint32_t nseg, xyzz_t<F>* wsum) {
-    typedef quad_ops<F> Q;
-    constexpr int NQ = THREADS / 4;
-    __shared__ xyzz_t<F> sh[NQ];
-    const uint32_t qid = threadIdx.x >> 2, ql = threadIdx.x & 3;
+    __shared__ xyzz_t<F> sh[THREADS];
     const xyzz_t<F>* p = partials + (size_t)blockIdx.x * nseg;
     xyzz_t<F> acc = xyzz_t<F>::identity();
-    for (uint32_t i = qid; i < nseg; i += NQ) acc = Q::add(acc, ld16(p + i));
-    if (ql == 0) sh[qid] = acc;
+    for (uint32_t i = threadIdx.x; i < nseg; i += THREADS) acc = add_sel<F>(acc, ld16(p + i));
+    sh[threadIdx.x] = acc;
     __syncthreads();
-    for (int s = NQ / 2; s > 0; s >>= 1) {
-        if ((int)qid < s) {
-            xyzz_t<F> a = sh[qid], b = sh[qid + s];
-            a = Q::add(a, b);
-            __syncwarp(Q::quad_mask());
-            if (ql == 0) sh[qid] = a;
+    for (int s = THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) {
+            xyzz_t<F> a = sh[threadIdx.x], b = sh[threadIdx.x + s];
+            sh[threadIdx.x] = add_sel<F>(a, b);
         }
         __syncthreads();
     }
     if (threadIdx.x == 0) st16(wsum + blockIdx.x, sh[0]);
 }
 
-// 6. Horner over windows (one quad)
+// 6. Horner over windows: ONE warp, its 8 quads run the same chain redundantly so that the quad shuffles can use
+// the full mask (quad_ops<F, true>)
 template <class F>
-__global__ void k_msm_combine(const xyzz_t<F>* wsum, uint32_t W, uint32_t c, xyzz_t<F>* out) {
-    typedef quad_ops<F> Q;
-    if (threadIdx.x >= 4 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(32) k_msm_combine(const xyzz_t<F>* wsum, uint32_t W, uint32_t c, xyzz_t<F>* out) {
+    typedef quad_ops<F, true> Q;
+    if (blockIdx.x != 0) return;
     xyzz_t<F> total = ld16(wsum + (W - 1));
     for (int w = (int)W - 2; w >= 0; --w) {
         for (uint32_t k = 0; k < c; ++k) total = Q::dbl(total);
@@ -499,13 +501,13 @@ static int msm_dev_impl(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const vo
     B2_TRY(check_launch(ctx, "k_msm_reduce_segments"));
     {
         LaunchScope ls(ctx, st, "msm_window_sum");
-        constexpr int T = 256;
+        constexpr int T = sizeof(F) > 32 ? 128 : 256;
         k_msm_window_sum<F, T><<<W, T, 0, st>>>(partials, nseg, wsum);
     }
     B2_TRY(check_launch(ctx, "k_msm_window_sum"));
     {
         LaunchScope ls(ctx, st, "msm_combine");
-        k_msm_combine<F><<<1, 4, 0, st>>>(wsum, W, c, out);
+        k_msm_combine<F><<<1, 32, 0, st>>>(wsum, W, c, out);
     }
     return check_launch(ctx, "k_msm_combine");
 }

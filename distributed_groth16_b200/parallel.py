@@ -1,0 +1,158 @@
+"""Multi-GPU orchestration (one process per GPU, `torch.distributed`): the replacement of the
+reference's king/client star (/root/reference/mpc-net/src/lib.rs:61-139, used by every `d_*` primitive
+through dist-primitives/src/channel/mod.rs:8-56) for the single-box setting.
+
+* MSM shards by index range; the only exchange is an all-gather of one XYZZ partial per rank.
+* NTT is a four-step (Bailey) transform: local column NTTs with the w_N^(col*k1) twiddle fused into
+  their last pass -> ONE all-to-all -> local row NTTs.  Distributed vectors live in the
+  "column layout": for a length-N vector and `ncols` columns, rank g of P owns the columns
+  n mod ncols in [g*ncols/P, (g+1)*ncols/P), each stored contiguously (N/ncols entries):
+      local[c][r] = x[r*ncols + g*ncols/P + c].
+  A transform with (rows, cols) maps layout(ncols = cols) -> layout(ncols = rows); chaining iNTT -> NTT
+  (the h pipeline) therefore needs no redistribution: the second transform swaps rows and cols.
+
+All field arithmetic is done by the CUDA library through a small backend object so that the host
+logic (index maps, collectives) can be exercised with the CPU oracle under gloo in tests/."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from ._native import c_vp
+
+
+# ---------------------------------------------------------------------------------------------
+# layout helpers (host side, numpy) -- used by callers to scatter/gather whole vectors and by tests
+# ---------------------------------------------------------------------------------------------
+def to_column_layout(x: np.ndarray, ncols: int, world: int, rank: int) -> np.ndarray:
+    """x: (N, 4) -> local (ncols/world, N/ncols, 4)."""
+    n = x.shape[0]
+    cg = ncols // world
+    m = x.reshape(n // ncols, ncols, 4)
+    return np.ascontiguousarray(m[:, rank * cg:(rank + 1) * cg].transpose(1, 0, 2))
+
+
+def from_column_layout(parts, ncols: int) -> np.ndarray:
+    """inverse of to_column_layout given every rank's local array (in rank order)."""
+    world = len(parts)
+    cg = ncols // world
+    rows = parts[0].shape[1]
+    out = np.empty((rows, ncols, 4), dtype=parts[0].dtype)
+    for g, p in enumerate(parts):
+        out[:, g * cg:(g + 1) * cg] = np.asarray(p).transpose(1, 0, 2)
+    return out.reshape(rows * ncols, 4)
+
+
+def split_log(log_n: int):
+    """(log_rows, log_cols) of the four-step split: rows >= cols."""
+    return (log_n + 1) // 2, log_n // 2
+
+
+# ---------------------------------------------------------------------------------------------
+# compute backend on the GPU (the only product backend)
+# ---------------------------------------------------------------------------------------------
+class GpuBackend:
+    def __init__(self, net):
+        self.net = net
+
+    def batched_ntt_post(self, x, log_t, batch, inverse, log_base=0, shift=False, b0=0, alpha=0, beta=0, gamma=0,
+                         post=True):
+        import torch
+        net = self.net
+        out = torch.empty_like(x)
+        if not post:
+            net.check(net._lib.b200zk_ntt_fr_dev(net._h, 0, c_vp(x.data_ptr()), c_vp(out.data_ptr()), log_t, int(inverse),
+                                                 0, batch))
+        else:
+            net.check(net._lib.b200zk_ntt_fr_batched_post_dev(net._h, 0, c_vp(x.data_ptr()), c_vp(out.data_ptr()), log_t,
+                                                              batch, int(inverse), log_base, int(shift),
+                                                              ctypes.c_uint64(b0), ctypes.c_uint64(alpha),
+                                                              ctypes.c_uint64(beta), ctypes.c_uint64(gamma)))
+        return out
+
+    def mul_sub(self, a, b, c):
+        import torch
+        net = self.net
+        out = torch.empty_like(a)
+        net.check(net._lib.b200zk_fr_mul_sub_dev(net._h, 0, c_vp(a.data_ptr()), c_vp(b.data_ptr()), c_vp(c.data_ptr()),
+                                                 c_vp(out.data_ptr()), a.numel() // 4))
+        return out
+
+    def msm_partial(self, bases, scalars, g2=False):
+        return self.net.msm_dev(bases, scalars, g2=g2)
+
+    def sum_points(self, xyzz, count, g2=False):
+        return self.net.sum_points_dev(xyzz, count, g2=g2)
+
+
+# ---------------------------------------------------------------------------------------------
+# collectives
+# ---------------------------------------------------------------------------------------------
+def _world(group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def sharded_ntt(backend, local, log_rows: int, log_cols: int, inverse: bool = False, shift_log_m: int | None = None,
+                group=None):
+    """Four-step NTT of a length-2^(log_rows+log_cols) vector in layout(ncols = 2^log_cols).
+
+    local: (cols/P, rows, 4) int64 tensor.  Returns (rows/P, cols, 4) = layout(ncols = 2^log_rows) of the
+    transform.  shift_log_m: when set (inverse transforms of the h pipeline), output coefficient j is also
+    multiplied by w_{2m}^j, m = 2^shift_log_m (the odd-coset shift of ext_wit::h / CircomReduction)."""
+    import torch
+    import torch.distributed as dist
+    world, rank = _world(group)
+    rows, cols = 1 << log_rows, 1 << log_cols
+    assert rows % world == 0 and cols % world == 0, "rows and cols must be divisible by the number of GPUs"
+    cg, rl = cols // world, rows // world
+    assert tuple(local.shape) == (cg, rows, 4), (tuple(local.shape), (cg, rows, 4))
+    log_n = log_rows + log_cols
+    # 1+2: column transforms (size rows) with the twiddle w_N^((col0 + c) * k1) fused
+    y = backend.batched_ntt_post(local.reshape(cg * rows, 4), log_rows, cg, inverse, log_base=log_n, shift=False,
+                                 b0=rank * cg, alpha=1, beta=0, gamma=0)
+    # 3: all-to-all transpose: destination g' receives the k1 in [g'*rl, (g'+1)*rl) of all my columns
+    send = y.reshape(cg, world, rl, 4).permute(1, 0, 2, 3).contiguous()
+    if world > 1:
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=group)
+    else:
+        recv = send
+    rows_in = recv.reshape(world, cg, rl, 4).permute(2, 0, 1, 3).contiguous()       # [k1 local][n2 global]
+    # 4: row transforms (size cols); optional coefficient shift w_2m^(k1 + rows*k2)
+    if shift_log_m is None:
+        out = backend.batched_ntt_post(rows_in.reshape(rl * cols, 4), log_cols, rl, inverse, post=False)
+    else:
+        out = backend.batched_ntt_post(rows_in.reshape(rl * cols, 4), log_cols, rl, inverse, log_base=shift_log_m + 1,
+                                       shift=True, b0=rank * rl, alpha=0, beta=1, gamma=rows)
+    return out.reshape(rl, cols, 4)
+
+
+def sharded_h(backend, a, b, c, log_m: int, group=None):
+    """ext_wit::h (groth16/src/ext_wit.rs:16-101) on vectors in layout(ncols = 2^log_cols), (log_rows, log_cols) =
+    split_log(log_m); returns h in the same layout.  One all-to-all per transform, six transforms (the 3+3 of
+    ext_wit.rs:34-52, with the 2m-domain evaluation replaced by the coefficient shift of CircomReduction)."""
+    log_rows, log_cols = split_log(log_m)
+    ev = []
+    for v in (a, b, c):
+        coef = sharded_ntt(backend, v, log_rows, log_cols, inverse=True, shift_log_m=log_m, group=group)
+        ev.append(sharded_ntt(backend, coef, log_cols, log_rows, inverse=False, group=group))
+    return backend.mul_sub(ev[0], ev[1], ev[2])
+
+
+def sharded_msm(backend, bases, scalars, g2: bool = False, group=None):
+    """d_msm over length-sharded inputs: local Pippenger, all-gather of the XYZZ partials, local point sum
+    (replaces send_to_king / unpackexp / recv_from_king, dist-primitives/src/dmsm/mod.rs:87-97)."""
+    import torch
+    import torch.distributed as dist
+    world, _ = _world(group)
+    part = backend.msm_partial(bases, scalars, g2)
+    if world > 1:
+        gathered = torch.empty((world, part.numel()), dtype=part.dtype, device=part.device)
+        dist.all_gather_into_tensor(gathered, part.reshape(1, -1), group=group)
+    else:
+        gathered = part.reshape(1, -1)
+    return backend.sum_points(gathered, world, g2)
