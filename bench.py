@@ -116,6 +116,52 @@ def run_reference(args):
     }))
 
 
+def measure_prove(net, args, with_cpu):
+    """Secondary metric of BASELINE.json: Groth16 prove ms, BN254, 2^20 constraints (m = n_vars = 2^20, dummy CRS
+    built like groth16/examples/local_groth_bench.rs:21-52; witness and QAP evaluations resident in HBM)."""
+    import numpy as np
+    import torch
+    from distributed_groth16_b200.groth16 import ProvingKey, prove
+    log_m = int(os.environ.get("B200ZK_BENCH_PROVE_LOG_M", "20"))
+    m = 1 << log_m
+    n_vars, n_inputs = m, 2
+    aq, b1 = net.generate_g1(101, n_vars), net.generate_g1(102, n_vars)
+    b2 = net.generate_g2(103, n_vars)
+    lq, hq = net.generate_g1(104, n_vars - n_inputs), net.generate_g1(105, m)
+    vk = np.concatenate([net.generate_g1(106, 3).cpu().numpy().view(np.uint64).reshape(-1),
+                         net.generate_g2(107, 2).cpu().numpy().view(np.uint64).reshape(-1)])
+    z = net.generate_fr(108, n_vars)
+    from distributed_groth16_b200._constants import FR_ONE_MONT
+    z[0] = torch.from_numpy(np.array(FR_ONE_MONT, dtype=np.uint64).view(np.int64)).to(z.device)
+    a, b, c = (net.generate_fr(sd, m) for sd in (109, 110, 111))
+    pk = ProvingKey.from_device(net, aq, b1, b2, lq, hq, n_inputs, vk)
+    times = []
+    proof = None
+    for _ in range(2 + 5):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        proof = prove.create_proof_dev(pk, z, a, b, c)         # returns after the 128 proof bytes are on the host
+        times.append((time.perf_counter() - t0) * 1e3)
+    times = sorted(times[2:])
+    res = {"metric": "Groth16 prove (BN254, 2^%d constraints, r = s = 0)" % log_m, "ms": times[len(times) // 2],
+           "ms_min": times[0], "unit": "ms", "higher_is_better": False, "n_vars": n_vars, "domain": m,
+           "msm_sizes": {"g1": [n_vars - 1, n_vars - n_inputs, m], "g2": [n_vars - 1]},
+           "timing": "host wall clock around b200zk_groth16_prove_dev (includes the D2H of the proof), 5 runs after 2 warm-ups"}
+    if with_cpu:
+        from oracle import cref
+        ncores = os.cpu_count() or 1
+        h2 = lambda t: t.cpu().numpy().view(np.uint64)
+        t0 = time.perf_counter()
+        hh = cref.h_circom(h2(a), h2(b), h2(c), ncores)
+        exp = cref.groth16_prove(h2(aq), h2(b1), h2(b2), h2(lq), h2(hq), vk, n_inputs, h2(z), hh, np.zeros(4, np.uint64),
+                                 np.zeros(4, np.uint64), nthreads=ncores)
+        res["cpu_baseline"] = {"ms": (time.perf_counter() - t0) * 1e3, "cores": ncores, "kind": "port",
+                               "sample": "one full prove (h + 4 MSMs) with the CPU restatement"}
+        res["bit_exact_vs_cpu"] = bool(exp == proof)
+    pk.free()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -123,6 +169,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prove", action="store_true", help="skip the secondary Groth16-prove measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -277,6 +324,8 @@ def main():
         out["cpu_baseline"] = {"value": n / dt / 1e6, "unit": UNIT, "cores": ncores, "kind": "port",
                                "sample": "one full 2^%d-pair G1 MSM, all host threads (%.2f s)" % (LOG_N, dt),
                                "bit_exact_vs_gpu": bool(world == 1 and (exp == res[0]).all()) if world == 1 else None}
+    if world == 1 and not args.no_prove:
+        out["prove"] = measure_prove(net, args, not args.no_cpu_baseline)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -60,6 +60,9 @@ SIGNATURES = {
     "b200zk_h_circom_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_uint, c_vp]),
     "b200zk_pk_upload": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t, ctypes.c_size_t,
                                         ctypes.c_size_t, c_vp, ctypes.POINTER(c_vp)]),
+    "b200zk_pk_upload_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t, ctypes.c_size_t,
+                                            ctypes.c_size_t, c_vp, ctypes.POINTER(c_vp)]),
+    "b200zk_groth16_prove_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp]),
     "b200zk_pk_free": (None, [c_vp, c_vp]),
     "b200zk_groth16_prove": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp]),
     "b200zk_g1_generate_dev": (ctypes.c_int, [c_vp, ctypes.c_uint64, ctypes.c_size_t, c_vp]),

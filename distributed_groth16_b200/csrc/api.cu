@@ -294,32 +294,45 @@ int b200zk_h_circom(b200zk_ctx* ctx, const uint64_t* a, const uint64_t* b, const
 }
 
 // ---- proving key + prove -----------------------------------------------------------------------
-static int upload(b200zk_ctx* ctx, void** dst, const void* src, size_t bytes) {
+static int upload(b200zk_ctx* ctx, void** dst, const void* src, size_t bytes, cudaMemcpyKind kind = cudaMemcpyHostToDevice) {
     *dst = nullptr;
-    if (bytes == 0) bytes = 16;
-    B2_CUDA_OK(ctx, cudaMalloc(dst, bytes + 16));
-    if (src) B2_CUDA_OK(ctx, cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice));
+    size_t alloc = bytes == 0 ? 16 : bytes;
+    B2_CUDA_OK(ctx, cudaMalloc(dst, alloc + 16));
+    if (src && bytes) B2_CUDA_OK(ctx, cudaMemcpy(*dst, src, bytes, kind));
     return B200ZK_OK;
 }
 
-int b200zk_pk_upload(b200zk_ctx* ctx, const uint64_t* a_query, const uint64_t* b_g1_query, const uint64_t* b_g2_query,
-                     const uint64_t* l_query, const uint64_t* h_query, size_t n_vars, size_t n_inputs, size_t m,
-                     const uint64_t* vk_points, b200zk_pk** out) {
+static int pk_build(b200zk_ctx* ctx, const void* a_query, const void* b_g1_query, const void* b_g2_query, const void* l_query,
+                    const void* h_query, size_t n_vars, size_t n_inputs, size_t m, const uint64_t* vk_points,
+                    cudaMemcpyKind kind, b200zk_pk** out) {
     if (!ctx || !out || !a_query || !b_g1_query || !b_g2_query || !h_query || !vk_points) return B200ZK_ERR_ARG;
     if (n_vars == 0 || n_inputs == 0 || n_inputs > n_vars) return set_error(ctx, B200ZK_ERR_ARG, "need 1 <= n_inputs <= n_vars");
     if (m == 0 || (m & (m - 1))) return set_error(ctx, B200ZK_ERR_DOMAIN, "h_query length must be a power of two");
     B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     b200zk_pk* pk = new b200zk_pk();
     pk->n_vars = n_vars; pk->n_inputs = n_inputs; pk->m = m;
-    int rc = upload(ctx, &pk->a_query, a_query, n_vars * 64);
-    if (!rc) rc = upload(ctx, &pk->b_g1_query, b_g1_query, n_vars * 64);
-    if (!rc) rc = upload(ctx, &pk->b_g2_query, b_g2_query, n_vars * 128);
-    if (!rc) rc = upload(ctx, &pk->l_query, l_query, (n_vars - n_inputs) * 64);
-    if (!rc) rc = upload(ctx, &pk->h_query, h_query, m * 64);
+    int rc = upload(ctx, &pk->a_query, a_query, n_vars * 64, kind);
+    if (!rc) rc = upload(ctx, &pk->b_g1_query, b_g1_query, n_vars * 64, kind);
+    if (!rc) rc = upload(ctx, &pk->b_g2_query, b_g2_query, n_vars * 128, kind);
+    if (!rc) rc = upload(ctx, &pk->l_query, l_query, (n_vars - n_inputs) * 64, kind);
+    if (!rc) rc = upload(ctx, &pk->h_query, h_query, m * 64, kind);
     if (!rc) rc = upload(ctx, &pk->vk, vk_points, 56 * 8);
     if (rc) { b200zk_pk_free(ctx, pk); return rc; }
     *out = pk;
     return B200ZK_OK;
+}
+
+int b200zk_pk_upload(b200zk_ctx* ctx, const uint64_t* a_query, const uint64_t* b_g1_query, const uint64_t* b_g2_query,
+                     const uint64_t* l_query, const uint64_t* h_query, size_t n_vars, size_t n_inputs, size_t m,
+                     const uint64_t* vk_points, b200zk_pk** out) {
+    return pk_build(ctx, a_query, b_g1_query, b_g2_query, l_query, h_query, n_vars, n_inputs, m, vk_points,
+                    cudaMemcpyHostToDevice, out);
+}
+int b200zk_pk_upload_dev(b200zk_ctx* ctx, const void* a_query, const void* b_g1_query, const void* b_g2_query,
+                         const void* l_query, const void* h_query, size_t n_vars, size_t n_inputs, size_t m,
+                         const uint64_t* vk_points, b200zk_pk** out) {
+    return pk_build(ctx, a_query, b_g1_query, b_g2_query, l_query, h_query, n_vars, n_inputs, m, vk_points,
+                    cudaMemcpyDeviceToDevice, out);
 }
 
 void b200zk_pk_free(b200zk_ctx* ctx, b200zk_pk* pk) {
@@ -345,6 +358,15 @@ int b200zk_groth16_prove(b200zk_ctx* ctx, const b200zk_pk* pk, const uint64_t* z
     B2_CUDA_OK(ctx, cudaMemcpyAsync(d_abc + m, b, m * sizeof(Fr), cudaMemcpyHostToDevice, sl.stream));
     B2_CUDA_OK(ctx, cudaMemcpyAsync(d_abc + 2 * m, c, m * sizeof(Fr), cudaMemcpyHostToDevice, sl.stream));
     return prove_dev(ctx, pk, d_z, d_abc, d_abc + m, d_abc + 2 * m, r, s, mirror_bg1, proof_out);
+}
+
+int b200zk_groth16_prove_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const void* d_z, const void* d_a, const void* d_b,
+                             const void* d_c, const uint64_t r[4], const uint64_t s[4], int mirror_bg1, uint8_t proof_out[128]) {
+    if (!ctx || !pk || !d_z || !d_a || !d_b || !d_c || !r || !s || !proof_out) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[0];
+    std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    return prove_dev(ctx, pk, (const Fr*)d_z, (const Fr*)d_a, (const Fr*)d_b, (const Fr*)d_c, r, s, mirror_bg1, proof_out);
 }
 
 // ---- generators / self-test --------------------------------------------------------------------

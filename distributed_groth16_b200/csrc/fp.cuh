@@ -357,22 +357,23 @@ struct Fq2 {
     B2_HD static Fq2 sub(const Fq2& a, const Fq2& b) { Fq2 r; r.c0 = Fq::sub(a.c0, b.c0); r.c1 = Fq::sub(a.c1, b.c1); return r; }
     B2_HD static Fq2 neg(const Fq2& a) { Fq2 r; r.c0 = Fq::neg(a.c0); r.c1 = Fq::neg(a.c1); return r; }
     B2_HD static Fq2 dbl(const Fq2& a) { return add(a, a); }
-    B2_HD static Fq2 mul(const Fq2& a, const Fq2& b) {
-        Fq v0 = Fq::mul_ni(a.c0, b.c0), v1 = Fq::mul_ni(a.c1, b.c1);
-        Fq s = Fq::mul_ni(Fq::add(a.c0, a.c1), Fq::add(b.c0, b.c1));
+    // one out-of-line unit per Fq2 product (3 inlined Fq products): 10 calls per mixed add instead of 28
+    B2_HD_NI static Fq2 mul(const Fq2& a, const Fq2& b) {
+        Fq v0 = Fq::mul(a.c0, b.c0), v1 = Fq::mul(a.c1, b.c1);
+        Fq s = Fq::mul(Fq::add(a.c0, a.c1), Fq::add(b.c0, b.c1));
         Fq2 r;
         r.c0 = Fq::sub(v0, v1);
         r.c1 = Fq::sub(Fq::sub(s, v0), v1);
         return r;
     }
-    B2_HD static Fq2 sqr(const Fq2& a) {
-        Fq t = Fq::mul_ni(Fq::add(a.c0, a.c1), Fq::sub(a.c0, a.c1));
-        Fq u = Fq::mul_ni(a.c0, a.c1);
+    B2_HD_NI static Fq2 sqr(const Fq2& a) {
+        Fq t = Fq::mul(Fq::add(a.c0, a.c1), Fq::sub(a.c0, a.c1));
+        Fq u = Fq::mul(a.c0, a.c1);
         Fq2 r; r.c0 = t; r.c1 = Fq::dbl(u); return r;
     }
-    B2_HD static Fq2 inv(const Fq2& a) {
-        Fq n = Fq::inv(Fq::add(Fq::mul_ni(a.c0, a.c0), Fq::mul_ni(a.c1, a.c1)));
-        Fq2 r; r.c0 = Fq::mul_ni(a.c0, n); r.c1 = Fq::neg(Fq::mul_ni(a.c1, n)); return r;
+    B2_HD_NI static Fq2 inv(const Fq2& a) {
+        Fq n = Fq::inv(Fq::add(Fq::sqr(a.c0), Fq::sqr(a.c1)));
+        Fq2 r; r.c0 = Fq::mul(a.c0, n); r.c1 = Fq::neg(Fq::mul(a.c1, n)); return r;
     }
 };
 

@@ -98,34 +98,60 @@ __global__ void k_prove_finalize(FinalizeArgs f) {
     compress_g1(C, f.out + 96);
 }
 
+// The five MSMs are spread over the three stream slots (the reference runs C's three d_msm on mux streams
+// 0/1/2 concurrently, prove.rs:119-125): slot 0 = h pipeline then MSM(h_query, h); slot 1 = the G2 MSM;
+// slot 2 = MSM(a_query) then MSM(l_query) (then MSM(b_g1_query)).  The latency-bound tails of one MSM
+// (bucket reduction, Horner) then overlap the throughput-bound bucket accumulation of another.
 int prove_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, const Fr* d_a, const Fr* d_b, const Fr* d_c,
               const uint64_t r[4], const uint64_t s[4], int mirror_bg1, uint8_t proof_out[128]) {
-    Slot& sl = ctx->slots[0];
-    cudaStream_t st = sl.stream;
+    Slot& s0 = ctx->slots[0];
+    Slot& s1 = ctx->slots[1];
+    Slot& s2 = ctx->slots[2];
+    std::lock_guard<std::mutex> g1(s1.mu);
+    std::lock_guard<std::mutex> g2(s2.mu);
+    cudaStream_t st = s0.stream;
     const size_t n1 = pk->n_vars - 1, n_aux = pk->n_vars - pk->n_inputs, m = pk->m;
     unsigned log_m = ceil_log2(m);
     if (((size_t)1 << log_m) != m) return set_error(ctx, B200ZK_ERR_DOMAIN, "h_query length must be a power of two");
     bool r_nonzero = (r[0] | r[1] | r[2] | r[3]) != 0;
     bool need_b1 = r_nonzero || mirror_bg1;
 
-    // small device block: 5 partials (3 G1 + 1 G2 + 1 G1) + r,s + 128-byte proof
+    // small device block: 5 partials (3 G1 + 1 G2 + 1 G1) + r,s + 128-byte proof, then the h vector
     const size_t o_a = 0, o_l = 128, o_h = 256, o_b1 = 384, o_b2 = 512, o_rs = 768, o_out = 832, o_hvec = 1024;
-    B2_CUDA_OK(ctx, sl.small.reserve(o_hvec + m * sizeof(Fr)));
-    char* sm = reinterpret_cast<char*>(sl.small.p);
+    B2_CUDA_OK(ctx, s0.small.reserve(o_hvec + m * sizeof(Fr)));
+    char* sm = reinterpret_cast<char*>(s0.small.p);
     Fr* d_h = reinterpret_cast<Fr*>(sm + o_hvec);
     uint64_t rs_host[8];
     memcpy(rs_host, r, 32); memcpy(rs_host + 4, s, 32);
     B2_CUDA_OK(ctx, cudaMemcpyAsync(sm + o_rs, rs_host, 64, cudaMemcpyHostToDevice, st));
 
-    B2_TRY(h_circom_dev(ctx, sl, d_a, d_b, d_c, log_m, d_h));
+    // inputs (z, a, b, c) were produced on slot 0's stream: the other slots wait for them
+    cudaEvent_t ev_in, ev1, ev2;
+    B2_CUDA_OK(ctx, cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming));
+    B2_CUDA_OK(ctx, cudaEventCreateWithFlags(&ev1, cudaEventDisableTiming));
+    B2_CUDA_OK(ctx, cudaEventCreateWithFlags(&ev2, cudaEventDisableTiming));
+    B2_CUDA_OK(ctx, cudaEventRecord(ev_in, st));
+    B2_CUDA_OK(ctx, cudaStreamWaitEvent(s1.stream, ev_in, 0));
+    B2_CUDA_OK(ctx, cudaStreamWaitEvent(s2.stream, ev_in, 0));
+
     const char* aq = reinterpret_cast<const char*>(pk->a_query);
     const char* b1q = reinterpret_cast<const char*>(pk->b_g1_query);
     const char* b2q = reinterpret_cast<const char*>(pk->b_g2_query);
-    B2_TRY(msm_g1_dev(ctx, sl, aq + 64, d_z + 1, n1, sm + o_a));
-    B2_TRY(msm_g2_dev(ctx, sl, b2q + 128, d_z + 1, n1, sm + o_b2));
-    B2_TRY(msm_g1_dev(ctx, sl, pk->l_query, d_z + pk->n_inputs, n_aux, sm + o_l));
-    B2_TRY(msm_g1_dev(ctx, sl, pk->h_query, d_h, m, sm + o_h));
-    if (need_b1) B2_TRY(msm_g1_dev(ctx, sl, b1q + 64, d_z + 1, n1, sm + o_b1));
+    int rc = msm_g2_dev(ctx, s1, b2q + 128, d_z + 1, n1, sm + o_b2);
+    if (!rc) rc = msm_g1_dev(ctx, s2, aq + 64, d_z + 1, n1, sm + o_a);
+    if (!rc) rc = msm_g1_dev(ctx, s2, pk->l_query, d_z + pk->n_inputs, n_aux, sm + o_l);
+    if (!rc && need_b1) rc = msm_g1_dev(ctx, s2, b1q + 64, d_z + 1, n1, sm + o_b1);
+    if (!rc) rc = h_circom_dev(ctx, s0, d_a, d_b, d_c, log_m, d_h);
+    if (!rc) rc = msm_g1_dev(ctx, s0, pk->h_query, d_h, m, sm + o_h);
+    cudaEventRecord(ev1, s1.stream);
+    cudaEventRecord(ev2, s2.stream);
+    cudaStreamWaitEvent(st, ev1, 0);
+    cudaStreamWaitEvent(st, ev2, 0);
+    if (rc) {
+        cudaStreamSynchronize(st);
+        cudaEventDestroy(ev_in); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
+        return rc;
+    }
 
     FinalizeArgs f;
     f.msm_a = sm + o_a; f.msm_b2 = sm + o_b2; f.msm_l = sm + o_l; f.msm_h = sm + o_h;
@@ -138,9 +164,13 @@ int prove_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, const Fr* d_a
         LaunchScope ls(ctx, st, "prove_finalize");
         k_prove_finalize<<<1, 32, 0, st>>>(f);
     }
-    B2_TRY(check_launch(ctx, "k_prove_finalize"));
-    B2_CUDA_OK(ctx, cudaMemcpyAsync(proof_out, sm + o_out, 128, cudaMemcpyDeviceToHost, st));
-    B2_CUDA_OK(ctx, cudaStreamSynchronize(st));
+    rc = check_launch(ctx, "k_prove_finalize");
+    cudaError_t e1 = cudaMemcpyAsync(proof_out, sm + o_out, 128, cudaMemcpyDeviceToHost, st);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaEventDestroy(ev_in); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
+    if (rc) return rc;
+    B2_CUDA_OK(ctx, e1);
+    B2_CUDA_OK(ctx, e2);
     return B200ZK_OK;
 }
 

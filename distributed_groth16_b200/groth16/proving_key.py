@@ -32,6 +32,26 @@ class ProvingKey:
                                             self.n_inputs, self.m, _ptr(vk), ctypes.byref(h)))
         self._h = h
 
+    @classmethod
+    def from_device(cls, net: Net, a_query, b_g1_query, b_g2_query, l_query, h_query, n_inputs: int, vk_points):
+        """Device-resident CUDA int64 tensors (e.g. a dummy CRS made by net.generate_g1/g2); vk_points: 56 host limbs."""
+        self = cls.__new__(cls)
+        self.net = net
+        self.n_vars = int(a_query.shape[0])
+        self.n_inputs = int(n_inputs)
+        self.m = int(h_query.shape[0])
+        self.host = None
+        vk = np.ascontiguousarray(vk_points, dtype=np.uint64).reshape(-1)
+        assert vk.size == 56
+        h = _native.c_vp()
+        lq_ptr = _native.c_vp(l_query.data_ptr()) if l_query.numel() else None
+        net.check(net._lib.b200zk_pk_upload_dev(net._h, _native.c_vp(a_query.data_ptr()), _native.c_vp(b_g1_query.data_ptr()),
+                                                _native.c_vp(b_g2_query.data_ptr()), lq_ptr,
+                                                _native.c_vp(h_query.data_ptr()), self.n_vars, self.n_inputs, self.m,
+                                                _ptr(vk), ctypes.byref(h)))
+        self._h = h
+        return self
+
     def free(self):
         if getattr(self, "_h", None) and self.net._h:
             self.net._lib.b200zk_pk_free(self.net._h, self._h)

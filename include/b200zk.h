@@ -116,6 +116,10 @@ int b200zk_h_circom_dev(b200zk_ctx* ctx, const void* d_a, const void* d_b, const
 int b200zk_pk_upload(b200zk_ctx* ctx, const uint64_t* a_query, const uint64_t* b_g1_query,
                      const uint64_t* b_g2_query, const uint64_t* l_query, const uint64_t* h_query, size_t n_vars,
                      size_t n_inputs, size_t m, const uint64_t* vk_points, b200zk_pk** out);
+/* Same, from device-resident arrays (copied device-to-device; the caller keeps ownership of its buffers). */
+int b200zk_pk_upload_dev(b200zk_ctx* ctx, const void* d_a_query, const void* d_b_g1_query, const void* d_b_g2_query,
+                         const void* d_l_query, const void* d_h_query, size_t n_vars, size_t n_inputs, size_t m,
+                         const uint64_t* vk_points, b200zk_pk** out);
 void b200zk_pk_free(b200zk_ctx* ctx, b200zk_pk* pk);
 
 /* ---- prove::{A,B,C}::compute + assembly (groth16/src/prove.rs:21-136, examples/sha256.rs:208-212)
@@ -126,6 +130,11 @@ void b200zk_pk_free(b200zk_ctx* ctx, b200zk_pk* pk);
 int b200zk_groth16_prove(b200zk_ctx* ctx, const b200zk_pk* pk, const uint64_t* z, const uint64_t* a,
                          const uint64_t* b, const uint64_t* c, const uint64_t r[4], const uint64_t s[4],
                          int mirror_bg1, uint8_t proof_out[128]);
+
+/* Same with z, a, b, c already resident in HBM. */
+int b200zk_groth16_prove_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const void* d_z, const void* d_a, const void* d_b,
+                             const void* d_c, const uint64_t r[4], const uint64_t s[4], int mirror_bg1,
+                             uint8_t proof_out[128]);
 
 /* ---- deterministic dummy inputs (groth16/examples/local_groth_bench.rs:21-52,
  *      groth16/src/proving_key.rs:112-155 generate dummy CRS points the same way: not a setup) ---- */
