@@ -213,6 +213,22 @@ class Net:
                                                int(inverse), int(coset), int(batch)))
         return out
 
+    def fr_convert(self, x, to_mont: bool, times: int = 1, sid: int = 0):
+        """Montgomery <-> canonical conversion of a CUDA int64 (n, 4) tensor, on the device."""
+        import torch
+        out = torch.empty_like(x)
+        self.check(self._lib.b200zk_fr_convert_dev(self._h, int(sid), c_vp(x.data_ptr()), c_vp(out.data_ptr()),
+                                                   x.numel() // 4, int(to_mont), int(times)))
+        return out
+
+    def to_device(self, arr):
+        """host (n, w) u64 array -> CUDA int64 tensor on this party's GPU."""
+        import torch
+        a = np.ascontiguousarray(arr)
+        if a.dtype == np.uint64:
+            a = a.view(np.int64)
+        return torch.from_numpy(a).to(self._dev())
+
     def h_circom_dev(self, a, b, c, out=None):
         import torch
         m = int(a.shape[0])

@@ -30,6 +30,11 @@ int b200zk_ctx_create(int device, b200zk_ctx** out) {
             return B200ZK_ERR_CUDA;
         }
         ctx->slots[i].owns_stream = true;
+        if (cudaStreamCreateWithFlags(&ctx->slots[i].copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->slots[i].copy_done, cudaEventDisableTiming) != cudaSuccess) {
+            delete ctx;
+            return B200ZK_ERR_CUDA;
+        }
     }
     *out = ctx;
     return B200ZK_OK;
@@ -44,6 +49,8 @@ void b200zk_ctx_destroy(b200zk_ctx* ctx) {
         Slot& s = ctx->slots[i];
         s.ws_msm.release(); s.ws_ntt.release(); s.io_a.release(); s.io_b.release(); s.small.release();
         if (s.owns_stream && s.stream) cudaStreamDestroy(s.stream);
+        if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
+        if (s.copy_done) cudaEventDestroy(s.copy_done);
     }
     for (auto& e : ctx->prof_pending) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
     delete ctx;
@@ -143,11 +150,14 @@ static int msm_host(b200zk_ctx* ctx, int stream, const uint64_t* bases, size_t n
     char* d_bases = reinterpret_cast<char*>(sl.io_a.p);
     char* d_scalars = d_bases + n * PB;
     if (n) {
-        B2_CUDA_OK(ctx, cudaMemcpyAsync(d_bases, bases, n * PB, cudaMemcpyHostToDevice, sl.stream));
+        // scalars first on the compute stream; the bases travel on the copy stream while digits/sort run
         B2_CUDA_OK(ctx, cudaMemcpyAsync(d_scalars, scalars, n * 32, cudaMemcpyHostToDevice, sl.stream));
+        B2_CUDA_OK(ctx, cudaMemcpyAsync(d_bases, bases, n * PB, cudaMemcpyHostToDevice, sl.copy_stream));
+        B2_CUDA_OK(ctx, cudaEventRecord(sl.copy_done, sl.copy_stream));
     }
     char* sm = reinterpret_cast<char*>(sl.small.p);
-    B2_TRY(G2 ? msm_g2_dev(ctx, sl, d_bases, d_scalars, n, sm) : msm_g1_dev(ctx, sl, d_bases, d_scalars, n, sm));
+    cudaEvent_t ready = n ? sl.copy_done : nullptr;
+    B2_TRY(G2 ? msm_g2_dev(ctx, sl, d_bases, d_scalars, n, sm, ready) : msm_g1_dev(ctx, sl, d_bases, d_scalars, n, sm, ready));
     B2_TRY(G2 ? g2_sum_dev(ctx, sl, sm, 1, sm + XB) : g1_sum_dev(ctx, sl, sm, 1, sm + XB));
     uint64_t host[17];
     B2_CUDA_OK(ctx, cudaMemcpyAsync(host, sm + XB, PB + 8, cudaMemcpyDeviceToHost, sl.stream));
@@ -291,6 +301,22 @@ int b200zk_h_circom(b200zk_ctx* ctx, const uint64_t* a, const uint64_t* b, const
     B2_CUDA_OK(ctx, cudaMemcpyAsync(h_out, d + 3 * m, m * sizeof(Fr), cudaMemcpyDeviceToHost, sl.stream));
     B2_CUDA_OK(ctx, cudaStreamSynchronize(sl.stream));
     return B200ZK_OK;
+}
+
+// ---- qap / conversions -------------------------------------------------------------------------
+int b200zk_qap_dev(b200zk_ctx* ctx, int stream, const void* a_ptr, const void* a_col, const void* a_val, const void* b_ptr,
+                   const void* b_col, const void* b_val, size_t nc, size_t n_inputs, const void* d_z, unsigned log_m, void* d_a,
+                   void* d_b, void* d_c) {
+    if (!ctx || !valid_slot(stream) || !a_ptr || !b_ptr || !d_z || !d_a || !d_b || !d_c) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[stream];
+    std::lock_guard<std::mutex> g(sl.mu);
+    return qap_dev(ctx, sl, a_ptr, a_col, a_val, b_ptr, b_col, b_val, nc, n_inputs, d_z, log_m, d_a, d_b, d_c);
+}
+int b200zk_fr_convert_dev(b200zk_ctx* ctx, int stream, const void* d_in, void* d_out, size_t n, int to_mont, int times) {
+    if (!ctx || !valid_slot(stream) || (n && (!d_in || !d_out)) || times < 0) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[stream];
+    std::lock_guard<std::mutex> g(sl.mu);
+    return fr_convert_dev(ctx, sl, d_in, d_out, n, to_mont, times);
 }
 
 // ---- proving key + prove -----------------------------------------------------------------------

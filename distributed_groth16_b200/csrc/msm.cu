@@ -385,7 +385,7 @@ static int exclusive_scan(b200zk_ctx* ctx, cudaStream_t st, const uint32_t* in, 
 
 template <class F>
 static int msm_dev_impl(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n, void* d_out,
-                        const char* acc_name) {
+                        const char* acc_name, cudaEvent_t bases_ready) {
     cudaStream_t st = sl.stream;
     xyzz_t<F>* out = reinterpret_cast<xyzz_t<F>*>(d_out);
     if (n == 0) {
@@ -483,6 +483,9 @@ static int msm_dev_impl(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const vo
         k_msm_scatter<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(keys, ranks, offsets, (uint32_t)n, total, entries);
     }
     B2_TRY(check_launch(ctx, "k_msm_scatter"));
+    // the digit / sort phases above only read the scalars: a caller staging host buffers lets the H2D copy of
+    // the (2-4x larger) base array overlap them and signals its arrival here
+    if (bases_ready) B2_CUDA_OK(ctx, cudaStreamWaitEvent(st, bases_ready, 0));
     {
         LaunchScope ls(ctx, st, acc_name);
         k_msm_accumulate<F><<<(unsigned)((max_tasks + 127) / 128), 128, 0, st>>>(
@@ -512,11 +515,13 @@ static int msm_dev_impl(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const vo
     return check_launch(ctx, "k_msm_combine");
 }
 
-int msm_g1_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n, void* d_out) {
-    return msm_dev_impl<Fq>(ctx, sl, d_bases, d_scalars, n, d_out, "msm_accumulate_g1");
+int msm_g1_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n, void* d_out,
+               cudaEvent_t bases_ready) {
+    return msm_dev_impl<Fq>(ctx, sl, d_bases, d_scalars, n, d_out, "msm_accumulate_g1", bases_ready);
 }
-int msm_g2_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n, void* d_out) {
-    return msm_dev_impl<Fq2>(ctx, sl, d_bases, d_scalars, n, d_out, "msm_accumulate_g2");
+int msm_g2_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n, void* d_out,
+               cudaEvent_t bases_ready) {
+    return msm_dev_impl<Fq2>(ctx, sl, d_bases, d_scalars, n, d_out, "msm_accumulate_g2", bases_ready);
 }
 
 template <class F>

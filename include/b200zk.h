@@ -110,6 +110,17 @@ int b200zk_h_circom(b200zk_ctx* ctx, const uint64_t* a, const uint64_t* b, const
 int b200zk_h_circom_dev(b200zk_ctx* ctx, const void* d_a, const void* d_b, const void* d_c, unsigned log_m,
                         void* d_h_out);
 
+/* ---- qap::qap (groth16/src/qap.rs:44-91): R1CS matrices x full assignment -> QAP evaluation vectors ----
+ * A and B in CSR form (row_ptr: num_constraints + 1 x u32, col: nnz x u32 wire index, val: nnz x 4 limbs
+ * Montgomery), z: full assignment (Montgomery).  Writes a, b, c (2^log_m x 4 limbs each):
+ * a_i = <A_i, z>, b_i = <B_i, z>, c_i = a_i b_i for i < num_constraints; a[num_constraints + j] = z[j], j < num_inputs. */
+int b200zk_qap_dev(b200zk_ctx* ctx, int stream, const void* d_a_row_ptr, const void* d_a_col, const void* d_a_val,
+                   const void* d_b_row_ptr, const void* d_b_col, const void* d_b_val, size_t num_constraints,
+                   size_t num_inputs, const void* d_z, unsigned log_m, void* d_a, void* d_b, void* d_c);
+/* Montgomery <-> canonical conversion applied `times` times (zkey coefficients are stored times R^2:
+ * ark-circom/src/zkey.rs:333-338 -> to_mont = 0, times = 1; .wtns / .r1cs values: to_mont = 1, times = 1). */
+int b200zk_fr_convert_dev(b200zk_ctx* ctx, int stream, const void* d_in, void* d_out, size_t n, int to_mont, int times);
+
 /* ---- proving key (what PackedProvingKeyShare carries, groth16/src/proving_key.rs:19-25,48-65) -- */
 /* a_query, b_g1_query, b_g2_query: n_vars points; l_query: n_vars - n_inputs; h_query: m points.
  * vk_points = alpha_g1(8) beta_g1(8) delta_g1(8) beta_g2(16) delta_g2(16) limbs. */

@@ -114,3 +114,42 @@ def test_f1_real_zkey_prove_on_gpu_matches_golden_and_verifies(net):
     vk1, vk2 = layout.arr_to_g1(d["vk_g1"]), layout.arr_to_g2(d["vk_g2"])
     assert o.groth16_verify(vk1[0], vk2[0], vk2[2], vk2[1], layout.arr_to_g1(d["ic"]), [z[1]], A, B, C)
     pk.free()
+
+
+def test_qap_matvec_and_prove_from_zkey_wtns_bytes(net):
+    """SURVEY f1 + f2: zkey / wtns bytes -> product readers -> GPU qap() -> prove; QAP vectors vs the oracle's
+    qap(), proof bytes vs the committed (pairing-verified) golden."""
+    import json
+    import os
+    import sys
+    HERE = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, HERE)
+    import artefact_writer as aw
+    from oracle import bn254 as o, layout
+    from distributed_groth16_b200.groth16 import circom, qap as qapmod
+    d = np.load(os.path.join(HERE, "golden", "complex_circuit.zkey.pk.npz"))
+    exp = json.load(open(os.path.join(HERE, "golden", "complex_circuit_proof.json")))
+    n_vars, n_public, m, nc = (int(x) for x in d["dims"])
+    zkey_bytes = aw.write_zkey(d)
+    z_int = aw.f1_witness(n_vars)
+    wtns_bytes = aw.write_wtns(z_int)
+    pk, mats, zk = circom.load_zkey(net, zkey_bytes)
+    z = circom.load_witness(net, wtns_bytes)
+    assert (z.cpu().numpy().view(np.uint64) == layout.fr_to_arr(z_int)).all()
+    q = qapmod.qap(mats, z, net)
+    vals_a, vals_b = layout.arr_to_fr(d["a_vals"]), layout.arr_to_fr(d["b_vals"])
+    ma = [[] for _ in range(nc)]
+    mb = [[] for _ in range(nc)]
+    for r_, c_, v in zip(d["a_rows"], d["a_cols"], vals_a):
+        ma[int(r_)].append((v, int(c_)))
+    for r_, c_, v in zip(d["b_rows"], d["b_cols"], vals_b):
+        mb[int(r_)].append((v, int(c_)))
+    ea, eb, ec = o.qap(ma, mb, n_public + 1, nc, z_int)
+    assert q.domain.size() == m == len(ea)
+    for got, want in ((q.a, ea), (q.b, eb), (q.c, ec)):
+        assert (got.cpu().numpy().view(np.uint64) == layout.fr_to_arr(want)).all()
+    assert circom.prove_from_matrices(pk, mats, z).hex() == exp["r0s0"]["proof_hex"]
+    proof, public = circom.prove_zkey_wtns(net, zkey_bytes, wtns_bytes)
+    assert proof.hex() == exp["r0s0"]["proof_hex"]
+    assert int.from_bytes(public[0].tobytes(), "little") == int(exp["public_input"])
+    pk.free()
