@@ -23,7 +23,17 @@ int b200zk_ctx_create(int device, b200zk_ctx** out) {
     b200zk_ctx* ctx = new b200zk_ctx();
     ctx->device = device;
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+        ctx->sm_count = prop.multiProcessorCount;
+        // keep the MSM base array resident in the 126 MB L2 while the bucket kernel gathers from it
+        const char* env = getenv("B200ZK_L2_PERSIST");
+        if (!(env && env[0] == '0') && prop.persistingL2CacheMaxSize > 0 &&
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize) == cudaSuccess) {
+            ctx->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+            ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+        }
+        cudaGetLastError();
+    }
     for (int i = 0; i < 3; ++i) {
         if (cudaStreamCreateWithFlags(&ctx->slots[i].stream, cudaStreamNonBlocking) != cudaSuccess) {
             delete ctx;
@@ -393,6 +403,21 @@ int b200zk_groth16_prove_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const void* d
     std::lock_guard<std::mutex> g(sl.mu);
     B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     return prove_dev(ctx, pk, (const Fr*)d_z, (const Fr*)d_a, (const Fr*)d_b, (const Fr*)d_c, r, s, mirror_bg1, proof_out);
+}
+
+int b200zk_xyzz_sum_dev(b200zk_ctx* ctx, int stream, int g2, const void* d_in, size_t count, size_t stride, void* d_out) {
+    if (!ctx || !valid_slot(stream) || !d_in || !d_out || count == 0) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[stream];
+    std::lock_guard<std::mutex> g(sl.mu);
+    return xyzz_sum_dev(ctx, sl, g2, d_in, count, stride, d_out);
+}
+int b200zk_groth16_assemble_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const void* d_msm_a, const void* d_msm_b2,
+                                const void* d_msm_l, const void* d_msm_h, const void* d_msm_b1, const uint64_t r[4],
+                                const uint64_t s[4], int include_zero_terms, uint8_t proof_out[128]) {
+    if (!ctx || !pk || !d_msm_a || !d_msm_b2 || !d_msm_l || !d_msm_h || !r || !s || !proof_out) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[0];
+    std::lock_guard<std::mutex> g(sl.mu);
+    return assemble_dev(ctx, sl, pk, d_msm_a, d_msm_b2, d_msm_l, d_msm_h, d_msm_b1, r, s, include_zero_terms, proof_out);
 }
 
 // ---- generators / self-test --------------------------------------------------------------------

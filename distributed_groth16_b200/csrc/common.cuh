@@ -55,6 +55,8 @@ struct Slot {                 // one per MultiplexedStreamID
 struct b200zk_ctx {
     int device = 0;
     int sm_count = 148;
+    size_t l2_persist_max = 0;      // cudaLimitPersistingL2CacheSize granted at creation
+    size_t l2_window_max = 0;       // accessPolicyMaxWindowSize
     b200zk::Slot slots[3];
     std::string last_error;
     std::mutex err_mu;
@@ -162,6 +164,7 @@ int msm_g2_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_sca
                cudaEvent_t bases_ready = nullptr);
 int g1_sum_dev(b200zk_ctx* ctx, Slot& sl, const void* d_xyzz, size_t count, void* d_out_affine);
 int g2_sum_dev(b200zk_ctx* ctx, Slot& sl, const void* d_xyzz, size_t count, void* d_out_affine);
+int xyzz_sum_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_in, size_t count, size_t stride, void* d_out);
 int generate_points_dev(b200zk_ctx* ctx, Slot& sl, int g2, uint64_t seed, size_t n, void* d_out);
 int generate_fr_dev(b200zk_ctx* ctx, Slot& sl, uint64_t seed, size_t n, void* d_out);
 int field_op_dev(b200zk_ctx* ctx, Slot& sl, int field, int op, const void* d_a, const void* d_b, void* d_out, size_t n);
@@ -171,6 +174,9 @@ int qap_dev(b200zk_ctx* ctx, Slot& sl, const void* a_ptr, const void* a_col, con
             const void* b_col, const void* b_val, size_t nc, size_t n_inputs, const void* d_z, unsigned log_m, void* d_a,
             void* d_b, void* d_c);
 // prove.cu
+int assemble_dev(b200zk_ctx* ctx, Slot& sl, const b200zk_pk* pk, const void* msm_a, const void* msm_b2, const void* msm_l,
+                 const void* msm_h, const void* msm_b1, const uint64_t r[4], const uint64_t s[4], int include_zero_terms,
+                 uint8_t proof_out[128]);
 int prove_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, const Fr* d_a, const Fr* d_b, const Fr* d_c,
               const uint64_t r[4], const uint64_t s[4], int mirror_bg1, uint8_t proof_out[128]);
 

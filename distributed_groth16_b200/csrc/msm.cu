@@ -486,12 +486,34 @@ static int msm_dev_impl(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const vo
     // the digit / sort phases above only read the scalars: a caller staging host buffers lets the H2D copy of
     // the (2-4x larger) base array overlap them and signals its arrival here
     if (bases_ready) B2_CUDA_OK(ctx, cudaStreamWaitEvent(st, bases_ready, 0));
+    bool l2_window = false;
+    if (ctx->l2_persist_max && ctx->l2_window_max) {
+        // every base point is gathered once per window (W times per launch): pin the array in L2
+        size_t bytes = n * sizeof(affine_t<F>);
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        attr.accessPolicyWindow.base_ptr = const_cast<void*>(d_bases);
+        attr.accessPolicyWindow.num_bytes = bytes < ctx->l2_window_max ? bytes : ctx->l2_window_max;
+        double ratio = (double)ctx->l2_persist_max / (double)attr.accessPolicyWindow.num_bytes;
+        attr.accessPolicyWindow.hitRatio = ratio > 1.0 ? 1.0f : (float)ratio;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        l2_window = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+        cudaGetLastError();
+    }
     {
         LaunchScope ls(ctx, st, acc_name);
         k_msm_accumulate<F><<<(unsigned)((max_tasks + 127) / 128), 128, 0, st>>>(
             reinterpret_cast<const affine_t<F>*>(d_bases), entries, offsets, task_off, task_bucket, order, nb, buckets, task_sums);
     }
     B2_TRY(check_launch(ctx, "k_msm_accumulate"));
+    if (l2_window) {
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        attr.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaGetLastError();
+    }
     {
         LaunchScope ls(ctx, st, "msm_merge");
         k_msm_merge_tasks<F><<<2 * ctx->sm_count, 128, 0, st>>>(multi + 1, multi, task_off, task_sums, buckets);
@@ -522,6 +544,23 @@ int msm_g1_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_sca
 int msm_g2_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n, void* d_out,
                cudaEvent_t bases_ready) {
     return msm_dev_impl<Fq2>(ctx, sl, d_bases, d_scalars, n, d_out, "msm_accumulate_g2", bases_ready);
+}
+
+// out = sum of `count` XYZZ points at pts[i * stride] (no normalisation): combines gathered per-rank partials
+template <class F>
+__global__ void k_sum_xyzz(const xyzz_t<F>* pts, uint32_t count, uint32_t stride, xyzz_t<F>* out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    xyzz_t<F> acc = xyzz_t<F>::identity();
+    for (uint32_t i = 0; i < count; ++i) acc = xyzz_t<F>::add(acc, ld16(pts + (size_t)i * stride));
+    st16(out, acc);
+}
+int xyzz_sum_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_in, size_t count, size_t stride, void* d_out) {
+    {
+        LaunchScope ls(ctx, sl.stream, "point_sum");
+        if (g2) k_sum_xyzz<Fq2><<<1, 32, 0, sl.stream>>>((const xyzz_t<Fq2>*)d_in, (uint32_t)count, (uint32_t)stride, (xyzz_t<Fq2>*)d_out);
+        else k_sum_xyzz<Fq><<<1, 32, 0, sl.stream>>>((const xyzz_t<Fq>*)d_in, (uint32_t)count, (uint32_t)stride, (xyzz_t<Fq>*)d_out);
+    }
+    return check_launch(ctx, "k_sum_xyzz");
 }
 
 template <class F>

@@ -61,6 +61,7 @@ struct FinalizeArgs {
     const void* vk;                                          // alpha_g1 beta_g1 delta_g1 | beta_g2 delta_g2
     const Fr* rs;                                            // r, s (Montgomery)
     uint8_t* out;
+    int add_zero_terms;                                      // 0: the MSMs already covered index 0 (z[0] = 1)
 };
 
 __global__ void k_prove_finalize(FinalizeArgs f) {
@@ -74,12 +75,12 @@ __global__ void k_prove_finalize(FinalizeArgs f) {
 
     xyzz_t<Fq> d1 = xyzz_t<Fq>::from_affine(delta1);
     xyzz_t<Fq> A = ldp<xyzz_t<Fq>>(f.msm_a);
-    xyzz_t<Fq>::madd(A, ldp<affine_t<Fq>>(f.a0), false);
+    if (f.add_zero_terms) xyzz_t<Fq>::madd(A, ldp<affine_t<Fq>>(f.a0), false);
     xyzz_t<Fq>::madd(A, alpha, false);
     if (!r_zero) A = xyzz_t<Fq>::add(A, xyzz_t<Fq>::mul_scalar(d1, r.l));
 
     xyzz_t<Fq2> Bp = ldp<xyzz_t<Fq2>>(f.msm_b2);
-    xyzz_t<Fq2>::madd(Bp, ldp<affine_t<Fq2>>(f.b2_0), false);
+    if (f.add_zero_terms) xyzz_t<Fq2>::madd(Bp, ldp<affine_t<Fq2>>(f.b2_0), false);
     xyzz_t<Fq2>::madd(Bp, beta2, false);
     if (!s_zero) Bp = xyzz_t<Fq2>::add(Bp, xyzz_t<Fq2>::mul_scalar(xyzz_t<Fq2>::from_affine(delta2), s.l));
 
@@ -87,7 +88,7 @@ __global__ void k_prove_finalize(FinalizeArgs f) {
     if (!s_zero) C = xyzz_t<Fq>::add(C, xyzz_t<Fq>::mul_scalar(A, s.l));
     if (!r_zero) {
         xyzz_t<Fq> B1 = ldp<xyzz_t<Fq>>(f.msm_b1);
-        xyzz_t<Fq>::madd(B1, ldp<affine_t<Fq>>(f.b1_0), false);
+        if (f.add_zero_terms) xyzz_t<Fq>::madd(B1, ldp<affine_t<Fq>>(f.b1_0), false);
         xyzz_t<Fq>::madd(B1, beta1, false);
         if (!s_zero) B1 = xyzz_t<Fq>::add(B1, xyzz_t<Fq>::mul_scalar(d1, s.l));
         C = xyzz_t<Fq>::add(C, xyzz_t<Fq>::mul_scalar(B1, r.l));
@@ -160,6 +161,7 @@ int prove_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, const Fr* d_a
     f.vk = pk->vk;
     f.rs = reinterpret_cast<const Fr*>(sm + o_rs);
     f.out = reinterpret_cast<uint8_t*>(sm + o_out);
+    f.add_zero_terms = 1;
     {
         LaunchScope ls(ctx, st, "prove_finalize");
         k_prove_finalize<<<1, 32, 0, st>>>(f);
@@ -171,6 +173,37 @@ int prove_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, const Fr* d_a
     if (rc) return rc;
     B2_CUDA_OK(ctx, e1);
     B2_CUDA_OK(ctx, e2);
+    return B200ZK_OK;
+}
+
+// Final assembly from externally combined MSM results (multi-GPU prove: every rank contributes partial sums,
+// parallel.sharded_prove all-gathers and adds them).  include_zero_terms = 0 when the sharded MSMs ran over
+// index 0 as well (z[0] = 1 makes a_query[0] * z[0] the same term the driver adds, sha256.rs:208-212).
+int assemble_dev(b200zk_ctx* ctx, Slot& sl, const b200zk_pk* pk, const void* msm_a, const void* msm_b2, const void* msm_l,
+                 const void* msm_h, const void* msm_b1, const uint64_t r[4], const uint64_t s[4], int include_zero_terms,
+                 uint8_t proof_out[128]) {
+    cudaStream_t st = sl.stream;
+    bool r_nonzero = (r[0] | r[1] | r[2] | r[3]) != 0;
+    if (r_nonzero && !msm_b1) return set_error(ctx, B200ZK_ERR_ARG, "r != 0 needs the b_g1_query MSM");
+    B2_CUDA_OK(ctx, sl.small.reserve(1024));
+    char* sm = reinterpret_cast<char*>(sl.small.p);
+    uint64_t rs_host[8];
+    memcpy(rs_host, r, 32); memcpy(rs_host + 4, s, 32);
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(sm + 768, rs_host, 64, cudaMemcpyHostToDevice, st));
+    FinalizeArgs f;
+    f.msm_a = msm_a; f.msm_b2 = msm_b2; f.msm_l = msm_l; f.msm_h = msm_h; f.msm_b1 = msm_b1;
+    f.a0 = pk->a_query; f.b1_0 = pk->b_g1_query; f.b2_0 = pk->b_g2_query;
+    f.vk = pk->vk;
+    f.rs = reinterpret_cast<const Fr*>(sm + 768);
+    f.out = reinterpret_cast<uint8_t*>(sm + 832);
+    f.add_zero_terms = include_zero_terms;
+    {
+        LaunchScope ls(ctx, st, "prove_finalize");
+        k_prove_finalize<<<1, 32, 0, st>>>(f);
+    }
+    B2_TRY(check_launch(ctx, "k_prove_finalize"));
+    B2_CUDA_OK(ctx, cudaMemcpyAsync(proof_out, sm + 832, 128, cudaMemcpyDeviceToHost, st));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(st));
     return B200ZK_OK;
 }
 

@@ -156,3 +156,67 @@ def sharded_msm(backend, bases, scalars, g2: bool = False, group=None):
     else:
         gathered = part.reshape(1, -1)
     return backend.sum_points(gathered, world, g2)
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-GPU prove (BASELINE config 5: MSM split + four-step NTT all-to-all)
+# ---------------------------------------------------------------------------------------------
+class ShardedProvingKey:
+    """The slice of a proving key one rank keeps resident.
+
+    a_query / b_g1_query / b_g2_query: rows [g*n_vars/P, (g+1)*n_vars/P) of the global arrays (rank 0's slice starts
+    with index 0); l_query: the same fraction of its n_vars - n_inputs rows; h_query: in the column layout of
+    `sharded_h` (local[c][r] = h_query[r*ncols + c0 + c], flattened), so that it lines up with the h this rank
+    computes.  vk_points: the 56 limbs of b200zk_pk_upload (replicated)."""
+
+    def __init__(self, net, a_query, b_g1_query, b_g2_query, l_query, h_query_cols, n_inputs, vk_points):
+        from .groth16.proving_key import ProvingKey
+        self.net = net
+        self.a_query, self.b_g1_query, self.b_g2_query = a_query, b_g1_query, b_g2_query
+        self.l_query, self.h_query = l_query, h_query_cols.reshape(-1, 8)
+        # the device-side pk object is only used for query[0] / vk in the final assembly
+        self.pk = ProvingKey.from_device(net, a_query[:1], b_g1_query[:1], b_g2_query[:1], a_query[:0], h_query_cols.reshape(-1, 8)[:1],
+                                         1, vk_points)
+
+
+def sharded_prove(net, spk: ShardedProvingKey, z_shard, z_aux_shard, a, b, c, log_m: int, r=None, s=None, group=None):
+    """Groth16 proof with every vector sharded over the ranks of `group`.
+
+    z_shard: this rank's rows of the full assignment (aligned with spk.a_query); z_aux_shard: its rows of
+    z[n_inputs:] (aligned with spk.l_query); a, b, c: QAP evaluations in the column layout (see sharded_ntt).
+    Every rank returns the same 128 bytes."""
+    import torch
+    import torch.distributed as dist
+    from ._native import c_vp
+    world, rank = _world(group)
+    be = GpuBackend(net)
+    zero = np.zeros(4, dtype=np.uint64)
+    r = zero if r is None else np.ascontiguousarray(r, dtype=np.uint64)
+    s = zero if s is None else np.ascontiguousarray(s, dtype=np.uint64)
+    need_b1 = bool(r.any())
+    h = sharded_h(be, a, b, c, log_m, group=group).reshape(-1, 4)
+    dev = z_shard.device
+    # slots: 0 A(G1) 1 L 2 H 3 B1 (each 16 words) then B2 (32 words)
+    parts = torch.zeros(4 * 16 + 32, dtype=torch.int64, device=dev)
+    net.msm_dev(spk.a_query, z_shard, parts[0:16])
+    net.msm_dev(spk.l_query, z_aux_shard, parts[16:32])
+    net.msm_dev(spk.h_query, h, parts[32:48])
+    if need_b1:
+        net.msm_dev(spk.b_g1_query, z_shard, parts[48:64])
+    net.msm_dev(spk.b_g2_query, z_shard, parts[64:96], g2=True)
+    if world > 1:
+        gathered = torch.empty((world, parts.numel()), dtype=parts.dtype, device=dev)
+        dist.all_gather_into_tensor(gathered, parts.reshape(1, -1), group=group)
+    else:
+        gathered = parts.reshape(1, -1)
+    tot = torch.empty_like(parts)
+    lib, hnd = net._lib, net._h
+    for k in range(4):        # G1 slots: stride between ranks = 96 words = 6 G1-XYZZ points
+        net.check(lib.b200zk_xyzz_sum_dev(hnd, 0, 0, c_vp(gathered.data_ptr() + k * 128), world, 6, c_vp(tot.data_ptr() + k * 128)))
+    net.check(lib.b200zk_xyzz_sum_dev(hnd, 0, 1, c_vp(gathered.data_ptr() + 512), world, 3, c_vp(tot.data_ptr() + 512)))
+    out = (ctypes.c_uint8 * 128)()
+    base = tot.data_ptr()
+    net.check(lib.b200zk_groth16_assemble_dev(hnd, spk.pk._h, c_vp(base), c_vp(base + 512), c_vp(base + 128), c_vp(base + 256),
+                                              c_vp(base + 384) if need_b1 else None, c_vp(r.ctypes.data), c_vp(s.ctypes.data),
+                                              0, out))
+    return bytes(out)

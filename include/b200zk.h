@@ -147,6 +147,14 @@ int b200zk_groth16_prove_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const void* d
                              const void* d_c, const uint64_t r[4], const uint64_t s[4], int mirror_bg1,
                              uint8_t proof_out[128]);
 
+/* Multi-GPU prove building blocks: sum `count` XYZZ partials spaced `stride` points apart into one XYZZ point,
+ * and run only the final assembly (prove.rs:36-44,75-83,128-134 + sha256.rs:208-212 + Compress::Yes) on MSM results
+ * that were combined across ranks.  include_zero_terms = 0 when the MSMs already covered index 0 (z[0] = 1). */
+int b200zk_xyzz_sum_dev(b200zk_ctx* ctx, int stream, int g2, const void* d_in, size_t count, size_t stride, void* d_out);
+int b200zk_groth16_assemble_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const void* d_msm_a, const void* d_msm_b2,
+                                const void* d_msm_l, const void* d_msm_h, const void* d_msm_b1_or_null,
+                                const uint64_t r[4], const uint64_t s[4], int include_zero_terms, uint8_t proof_out[128]);
+
 /* ---- deterministic dummy inputs (groth16/examples/local_groth_bench.rs:21-52,
  *      groth16/src/proving_key.rs:112-155 generate dummy CRS points the same way: not a setup) ---- */
 int b200zk_g1_generate_dev(b200zk_ctx* ctx, uint64_t seed, size_t n, void* d_out);

@@ -82,3 +82,38 @@ def check_all(backend, to_dev, rank, world, log_m=6, msm_n=64):
     exp, einf = cref.msm_g1(bases, scalars)
     res["msm"] = bool(inf == einf and (got == exp).all())
     return res
+
+
+def check_sharded_prove(net, to_dev, rank, world, log_m=10, rs=(0, 0)):
+    """GPU backend only: sharded_prove on `world` ranks vs the CPU twin's proof for the same global instance."""
+    import torch
+    from oracle import cref, layout
+    m = 1 << log_m
+    n_vars, n_inputs = m, 2
+    log_rows, log_cols = par.split_log(log_m)
+    cols = 1 << log_cols
+    aq, b1, lq, hq = cref.g1_generate(201, n_vars), cref.g1_generate(202, n_vars), cref.g1_generate(204, n_vars - n_inputs), cref.g1_generate(205, m)
+    b2 = cref.g2_generate(203, n_vars)
+    vk1, vk2 = cref.g1_generate(206, 3), cref.g2_generate(207, 2)
+    vk = np.concatenate([vk1.reshape(-1), vk2.reshape(-1)])
+    z = cref.fr_generate(208, n_vars)
+    z[0] = layout.fr_to_arr([1])[0]
+    a, b, c = (cref.fr_generate(sd, m) for sd in (209, 210, 211))
+    r, s = layout.fr_to_arr([rs[0]])[0], layout.fr_to_arr([rs[1]])[0]
+    exp = cref.groth16_prove(aq, b1, b2, lq, hq, vk, n_inputs, z, cref.h_circom(a, b, c), r, s)
+    sl = slice(rank * n_vars // world, (rank + 1) * n_vars // world)
+    n_aux = n_vars - n_inputs
+    sl_aux = slice(rank * n_aux // world, (rank + 1) * n_aux // world)
+    spk = par.ShardedProvingKey(net, to_dev(aq[sl]), to_dev(b1[sl]), to_dev(b2[sl]), to_dev(lq[sl_aux]),
+                                to_dev(_cols_g1(hq, cols, world, rank)), n_inputs, vk)
+    la, lb, lc = (to_dev(par.to_column_layout(v, cols, world, rank)) for v in (a, b, c))
+    got = par.sharded_prove(net, spk, to_dev(z[sl]), to_dev(z[n_inputs:][sl_aux]), la, lb, lc, log_m, r, s)
+    return got == exp
+
+
+def _cols_g1(pts, ncols, world, rank):
+    """column layout for an (N, 8) point array (same index map as to_column_layout)."""
+    n = pts.shape[0]
+    cg = ncols // world
+    mview = pts.reshape(n // ncols, ncols, 8)
+    return np.ascontiguousarray(mview[:, rank * cg:(rank + 1) * cg].transpose(1, 0, 2))
