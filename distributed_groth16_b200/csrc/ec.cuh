@@ -124,6 +124,53 @@ struct xyzz_t {
         return r;
     }
 
+    // ---- latency-optimised variants: the independent products of each dependency level are issued as one
+    //      row-interleaved group (F::mul_group), 3 levels per doubling and 4 per addition -------------------
+    B2_HD static xyzz_t dbl_ilp(const xyzz_t& p) {
+        if (p.is_inf()) return p;
+        F U = F::dbl(p.y);
+        F a1[2] = {U, p.x}, b1[2] = {U, p.x}, r1[2];
+        F::template mul_group<2>(r1, a1, b1);                       // V = U^2, X2 = X^2
+        F V = r1[0];
+        F M = F::add(F::dbl(r1[1]), r1[1]);
+        F a2[4] = {U, p.x, V, M}, b2[4] = {V, V, p.zz, M}, r2[4];
+        F::template mul_group<4>(r2, a2, b2);                       // W, S, ZZ3, M^2
+        xyzz_t r;
+        r.x = F::sub(r2[3], F::dbl(r2[1]));
+        F a3[3] = {M, r2[0], r2[0]}, b3[3] = {F::sub(r2[1], r.x), p.y, p.zzz}, r3[3];
+        F::template mul_group<3>(r3, a3, b3);                       // M(S - X3), W Y, W ZZZ
+        r.y = F::sub(r3[0], r3[1]);
+        r.zz = r2[2];
+        r.zzz = r3[2];
+        return r;
+    }
+    B2_HD static xyzz_t add_ilp(const xyzz_t& a, const xyzz_t& b) {
+        if (a.is_inf()) return b;
+        if (b.is_inf()) return a;
+        F a1[4] = {a.x, b.x, a.y, b.y}, b1[4] = {b.zz, a.zz, b.zzz, a.zzz}, r1[4];
+        F::template mul_group<4>(r1, a1, b1);                       // U1, U2, S1, S2
+        F Pp = F::sub(r1[1], r1[0]), R = F::sub(r1[3], r1[2]);
+        if (Pp.is_zero()) {
+            if (R.is_zero()) return dbl(a);
+            return identity();
+        }
+        F a2[4] = {Pp, R, a.zz, a.zzz}, b2[4] = {Pp, R, b.zz, b.zzz}, r2[4];
+        F::template mul_group<4>(r2, a2, b2);                       // PP, R^2, ZZ1 ZZ2, ZZZ1 ZZZ2
+        F a3[3] = {Pp, r1[0], r2[2]}, b3[3] = {r2[0], r2[0], r2[0]}, r3[3];
+        F::template mul_group<3>(r3, a3, b3);                       // PPP, Q, ZZ3
+        xyzz_t r;
+        r.x = F::sub(F::sub(r2[1], r3[0]), F::dbl(r3[1]));
+        F a4[3] = {R, r1[2], r2[3]}, b4[3] = {F::sub(r3[1], r.x), r3[0], r3[0]}, r4[3];
+        F::template mul_group<3>(r4, a4, b4);                       // R(Q - X3), S1 PPP, ZZZ3
+        r.y = F::sub(r4[0], r4[1]);
+        r.zz = r3[2];
+        r.zzz = r4[2];
+        return r;
+    }
+
+    B2_HD_NI static xyzz_t dbl_ilp_ni(const xyzz_t& p) { return dbl_ilp(p); }
+    B2_HD_NI static xyzz_t add_ilp_ni(const xyzz_t& a, const xyzz_t& b) { return add_ilp(a, b); }
+
     B2_HD static xyzz_t neg(const xyzz_t& a) { xyzz_t r = a; r.y = F::neg(a.y); return r; }
 
     // canonical affine (x = X/ZZ, y = Y/ZZZ); infinity -> (0,0)

@@ -89,6 +89,16 @@ static int test_curve(const char* name, int is_g2) {
         if (memcmp(&ta, &ua, sizeof(ta))) { printf("%s: madd doubling path mismatch\n", name); return 1; }
         xyzz_t<F>::madd(t, p, true); xyzz_t<F>::madd(t, p, true);        // back to identity
         if (!t.is_inf()) { printf("%s: P + (-P) path mismatch\n", name); return 1; }
+        {   // latency-optimised (row-interleaved) group law == plain group law
+            affine_t<F> q; memcpy(&q, pts + PL * 9, PL * 8);
+            xyzz_t<F> v = xyzz_t<F>::dbl(xyzz_t<F>::from_affine(q));
+            xyzz_t<F> s1 = xyzz_t<F>::add(u, v), s2 = xyzz_t<F>::add_ilp(u, v);
+            xyzz_t<F> d1 = xyzz_t<F>::dbl(s1), d2 = xyzz_t<F>::dbl_ilp(s2);
+            if (memcmp(&s1, &s2, sizeof(s1)) || memcmp(&d1, &d2, sizeof(d1))) { printf("%s: ilp group law mismatch\n", name); return 1; }
+            xyzz_t<F> e1 = xyzz_t<F>::add_ilp(u, u), e2 = xyzz_t<F>::dbl(u);
+            affine_t<F> ea = xyzz_t<F>::to_affine(e1), eb = xyzz_t<F>::to_affine(e2);
+            if (memcmp(&ea, &eb, sizeof(ea))) { printf("%s: add_ilp equal-operands mismatch\n", name); return 1; }
+        }
         xyzz_t<F> w = xyzz_t<F>::add(u, u);                               // add with equal operands
         xyzz_t<F> w2 = xyzz_t<F>::dbl(u);
         affine_t<F> wa = xyzz_t<F>::to_affine(w), w2a = xyzz_t<F>::to_affine(w2);
