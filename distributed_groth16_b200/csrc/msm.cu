@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(128, B2_ACC_MINBLOCKS) k_msm_accumulate(const 
 
 template <class F>
 __device__ __forceinline__ xyzz_t<F> add_sel(const xyzz_t<F>& a, const xyzz_t<F>& b) {
-    if (sizeof(F) == 32) return xyzz_t<F>::add_ilp(a, b);      // G1: inline, row-interleaved products (latency-bound chains)
+    if (sizeof(F) == 32) return xyzz_t<F>::add_inl(a, b);      // G1: inline (see k_msm_reduce_segments)
     return xyzz_t<F>::add(a, b);
 }
 
@@ -290,16 +290,16 @@ __global__ void __launch_bounds__(128) k_msm_reduce_segments(const xyzz_t<F>* bu
     constexpr bool INL = sizeof(F) == 32;
     for (uint32_t k = lo + seg_len; k-- > lo;) {
         xyzz_t<F> bk = ld16(bw + k);
-        if (INL) { run = xyzz_t<F>::add_ilp(run, bk); acc = xyzz_t<F>::add_ilp(acc, run); }
+        if (INL) { run = xyzz_t<F>::add_inl(run, bk); acc = xyzz_t<F>::add_inl(acc, run); }
         else { run = xyzz_t<F>::add(run, bk); acc = xyzz_t<F>::add(acc, run); }
     }
     if (lo) {   // + lo * run
         xyzz_t<F> m = xyzz_t<F>::identity();
         for (int bit = 31 - __clz(lo); bit >= 0; --bit) {
-            if (INL) m = xyzz_t<F>::dbl_ilp(m); else m = xyzz_t<F>::dbl(m);
-            if ((lo >> bit) & 1) { if (INL) m = xyzz_t<F>::add_ilp(m, run); else m = xyzz_t<F>::add(m, run); }
+            if (INL) m = xyzz_t<F>::dbl_inl(m); else m = xyzz_t<F>::dbl(m);
+            if ((lo >> bit) & 1) { if (INL) m = xyzz_t<F>::add_inl(m, run); else m = xyzz_t<F>::add(m, run); }
         }
-        if (INL) acc = xyzz_t<F>::add_ilp(acc, m); else acc = xyzz_t<F>::add(acc, m);
+        if (INL) acc = xyzz_t<F>::add_inl(acc, m); else acc = xyzz_t<F>::add(acc, m);
     }
     st16(partials + t, acc);
 }
@@ -323,19 +323,18 @@ __global__ void __launch_bounds__(THREADS) k_msm_window_sum(const xyzz_t<F>* par
     if (threadIdx.x == 0) st16(wsum + blockIdx.x, sh[0]);
 }
 
-// 6. Horner over windows: one thread, every doubling / addition issues its independent field products as
-// row-interleaved groups (xyzz_t::dbl_ilp / add_ilp).  (A quad-cooperative version -- 4 lanes sharing one point
-// operation through shuffles -- measured 0.87 ms at c = 16; the interleaved single-thread chain is faster.)
+// 6. Horner over windows: ONE warp, its 8 quads run the same chain redundantly so that the quad shuffles can use
+// the full mask (quad_ops<F, true>)
 template <class F>
 __global__ void __launch_bounds__(32) k_msm_combine(const xyzz_t<F>* wsum, uint32_t W, uint32_t c, xyzz_t<F>* out) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    constexpr bool G1 = sizeof(F) == 32;
+    typedef quad_ops<F, true> Q;
+    if (blockIdx.x != 0) return;
     xyzz_t<F> total = ld16(wsum + (W - 1));
     for (int w = (int)W - 2; w >= 0; --w) {
-        for (uint32_t k = 0; k < c; ++k) total = G1 ? xyzz_t<F>::dbl_ilp(total) : xyzz_t<F>::dbl_ilp_ni(total);
-        total = G1 ? xyzz_t<F>::add_ilp(total, ld16(wsum + w)) : xyzz_t<F>::add_ilp_ni(total, ld16(wsum + w));
+        for (uint32_t k = 0; k < c; ++k) total = Q::dbl(total);
+        total = Q::add(total, ld16(wsum + w));
     }
-    st16(out, total);
+    if (threadIdx.x == 0) st16(out, total);
 }
 
 // sum `count` XYZZ points, normalise; out = affine followed by one u64 infinity flag
