@@ -52,6 +52,13 @@ SIGNATURES = {
                                          ctypes.c_uint]),
     "b200zk_ntt_fr_fourstep_cols_dev": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_uint, ctypes.c_uint,
                                                        ctypes.c_uint, ctypes.c_uint64, ctypes.c_int]),
+    "b200zk_ntt_fr_fourstep_cols_p2p_dev": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, ctypes.POINTER(c_vp), ctypes.c_uint,
+                                                           ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint64,
+                                                           ctypes.c_int]),
+    "b200zk_peer_alloc": (ctypes.c_int, [c_vp, ctypes.c_size_t, ctypes.POINTER(c_vp), c_vp]),
+    "b200zk_peer_open": (ctypes.c_int, [c_vp, c_vp, ctypes.POINTER(c_vp)]),
+    "b200zk_peer_close": (ctypes.c_int, [c_vp, c_vp]),
+    "b200zk_peer_free": (ctypes.c_int, [c_vp, c_vp]),
     "b200zk_ntt_fr_batched_post_dev": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_uint, ctypes.c_uint,
                                                       ctypes.c_int, ctypes.c_uint, ctypes.c_int, ctypes.c_uint64,
                                                       ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64]),

@@ -270,6 +270,45 @@ int b200zk_ntt_fr_fourstep_cols_dev(b200zk_ctx* ctx, int stream, const void* d_i
                              log_cols_local, log_n, global_col0, inverse != 0);
 }
 
+int b200zk_ntt_fr_fourstep_cols_p2p_dev(b200zk_ctx* ctx, int stream, const void* d_in, void* const* peer_out, unsigned n_peers,
+                                        unsigned log_rows, unsigned log_cols_local, unsigned log_n, uint64_t global_col0,
+                                        int inverse) {
+    if (!ctx || !valid_slot(stream) || !d_in || !peer_out) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[stream];
+    std::lock_guard<std::mutex> g(sl.mu);
+    return fourstep_cols_p2p_dev(ctx, sl, reinterpret_cast<const Fr*>(d_in), peer_out, n_peers, log_rows, log_cols_local, log_n,
+                                 global_col0, inverse != 0);
+}
+
+int b200zk_peer_alloc(b200zk_ctx* ctx, size_t bytes, void** d_ptr, uint8_t handle_out[64]) {
+    if (!ctx || !d_ptr || !handle_out || bytes == 0) return B200ZK_ERR_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    B2_CUDA_OK(ctx, cudaMalloc(d_ptr, bytes));
+    cudaIpcMemHandle_t h;
+    B2_CUDA_OK(ctx, cudaIpcGetMemHandle(&h, *d_ptr));
+    memcpy(handle_out, &h, 64);
+    return B200ZK_OK;
+}
+int b200zk_peer_open(b200zk_ctx* ctx, const uint8_t handle[64], void** d_ptr) {
+    if (!ctx || !d_ptr || !handle) return B200ZK_ERR_ARG;
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    B2_CUDA_OK(ctx, cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return B200ZK_OK;
+}
+int b200zk_peer_close(b200zk_ctx* ctx, void* d_ptr) {
+    if (!ctx || !d_ptr) return B200ZK_ERR_ARG;
+    B2_CUDA_OK(ctx, cudaIpcCloseMemHandle(d_ptr));
+    return B200ZK_OK;
+}
+int b200zk_peer_free(b200zk_ctx* ctx, void* d_ptr) {
+    if (!ctx || !d_ptr) return B200ZK_ERR_ARG;
+    B2_CUDA_OK(ctx, cudaFree(d_ptr));
+    return B200ZK_OK;
+}
+
 int b200zk_ntt_fr_batched_post_dev(b200zk_ctx* ctx, int stream, const void* d_in, void* d_out, unsigned log_t, unsigned batch,
                                    int inverse, unsigned log_base, int base_is_shift, uint64_t b0, uint64_t alpha,
                                    uint64_t beta, uint64_t gamma) {

@@ -155,6 +155,8 @@ int fourstep_cols_dev(b200zk_ctx* ctx, Slot& sl, const Fr* d_in, Fr* d_out, unsi
                       unsigned log_cols_local, unsigned log_n, uint64_t global_col0, bool inverse);
 int ntt_batched_post_dev(b200zk_ctx* ctx, Slot& sl, const Fr* d_in, Fr* d_out, unsigned log_t, unsigned batch, bool inverse,
                          unsigned log_base, bool base_is_shift, uint64_t b0, uint64_t alpha, uint64_t beta, uint64_t gamma);
+int fourstep_cols_p2p_dev(b200zk_ctx* ctx, Slot& sl, const Fr* d_in, void* const* peer_out, unsigned n_peers, unsigned log_rows,
+                          unsigned log_cols_local, unsigned log_n, uint64_t global_col0, bool inverse);
 int mul_sub_dev(b200zk_ctx* ctx, Slot& sl, const Fr* a, const Fr* b, const Fr* c, Fr* out, size_t n);
 void ntt_free_plans(b200zk_ctx* ctx);
 // msm.cu

@@ -216,13 +216,22 @@ struct quad_ops {
     __device__ __forceinline__ static unsigned quad_mask() { return FULLWARP ? 0xFFFFFFFFu : (0xFu << (threadIdx.x & 28u)); }
     __device__ __forceinline__ static int quad_lane() { return threadIdx.x & 3; }
 
-    __device__ __forceinline__ static F bcast(const F& v, int src) {
-        F r;
-        const uint32_t* pv = reinterpret_cast<const uint32_t*>(&v);
-        uint32_t* pr = reinterpret_cast<uint32_t*>(&r);
-        const unsigned m = quad_mask();
+    // exchange area in shared memory: 2 buffers x 4 products per quad (double-buffered: one __syncwarp per level).
+    // Shuffles were measured slower here: with data-dependent branches upstream every SHFL gets wrapped in a
+    // WARPSYNC/collective sequence (576 SHFL + 320 WARPSYNC per doubling+addition in SASS).
+    struct xch_t { F p[2][4]; };
+    __device__ __forceinline__ static void put(F* dst, const F& v) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(&v);
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
-        for (int i = 0; i < WORDS; ++i) pr[i] = __shfl_sync(m, pv[i], src, 4);
+        for (int i = 0; i < (int)(sizeof(F) / 16); ++i) d4[i] = s4[i];
+    }
+    __device__ __forceinline__ static F get(const F* src) {
+        F r;
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        uint4* d4 = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(F) / 16); ++i) d4[i] = s4[i];
         return r;
     }
     __device__ __forceinline__ static F sel(int q, const F& a0, const F& a1, const F& a2, const F& a3) {
@@ -236,54 +245,59 @@ struct quad_ops {
         for (int i = 0; i < WORDS; ++i) pr[i] = q == 0 ? p0[i] : q == 1 ? p1[i] : q == 2 ? p2[i] : p3[i];
         return r;
     }
-    // p_k = a_k * b_k, lane k computing product k; every lane receives all four
-    __device__ __forceinline__ static void mul4(const F& a0, const F& b0, const F& a1, const F& b1, const F& a2, const F& b2,
-                                             const F& a3, const F& b3, F& p0, F& p1, F& p2, F& p3) {
+    // p_k = a_k * b_k, lane k computing product k; every lane receives all four through `x` (buffer `buf`)
+    __device__ __forceinline__ static void mul4(xch_t* x, int buf, const F& a0, const F& b0, const F& a1, const F& b1,
+                                                const F& a2, const F& b2, const F& a3, const F& b3, F& p0, F& p1, F& p2, F& p3) {
         const int q = quad_lane();
         F a = sel(q, a0, a1, a2, a3), b = sel(q, b0, b1, b2, b3);
         F p = F::mul(a, b);
-        p0 = bcast(p, 0); p1 = bcast(p, 1); p2 = bcast(p, 2); p3 = bcast(p, 3);
+        put(&x->p[buf][q], p);
+        __syncwarp(quad_mask());
+        p0 = get(&x->p[buf][0]); p1 = get(&x->p[buf][1]); p2 = get(&x->p[buf][2]); p3 = get(&x->p[buf][3]);
     }
 
-    __device__ static xyzz_t<F> dbl(const xyzz_t<F>& p) {
+    __device__ static xyzz_t<F> dbl(xch_t* x, const xyzz_t<F>& p) {
         if (p.is_inf()) return p;
         F U = F::dbl(p.y);
         F V, X2, d0, d1;
-        mul4(U, U, p.x, p.x, U, U, U, U, V, X2, d0, d1);
+        mul4(x, 0, U, U, p.x, p.x, U, U, U, U, V, X2, d0, d1);
         F M = F::add(F::dbl(X2), X2);
         F W, S, ZZ3, MM;
-        mul4(U, V, p.x, V, V, p.zz, M, M, W, S, ZZ3, MM);
+        mul4(x, 1, U, V, p.x, V, V, p.zz, M, M, W, S, ZZ3, MM);
         xyzz_t<F> r;
         r.x = F::sub(MM, F::dbl(S));
         F T1, T2, ZZZ3;
-        mul4(M, F::sub(S, r.x), W, p.y, W, p.zzz, W, W, T1, T2, ZZZ3, d0);
+        mul4(x, 0, M, F::sub(S, r.x), W, p.y, W, p.zzz, W, W, T1, T2, ZZZ3, d0);
         r.y = F::sub(T1, T2);
         r.zz = ZZ3;
         r.zzz = ZZZ3;
+        __syncwarp(quad_mask());          // buffer 1 is reused by the next operation's second level
         return r;
     }
 
-    __device__ static xyzz_t<F> add(const xyzz_t<F>& a, const xyzz_t<F>& b) {
+    __device__ static xyzz_t<F> add(xch_t* x, const xyzz_t<F>& a, const xyzz_t<F>& b) {
         if (a.is_inf()) return b;
         if (b.is_inf()) return a;
         F U1, U2, S1, S2;
-        mul4(a.x, b.zz, b.x, a.zz, a.y, b.zzz, b.y, a.zzz, U1, U2, S1, S2);
+        mul4(x, 0, a.x, b.zz, b.x, a.zz, a.y, b.zzz, b.y, a.zzz, U1, U2, S1, S2);
         F Pp = F::sub(U2, U1), R = F::sub(S2, S1);
         if (Pp.is_zero()) {
-            if (R.is_zero()) return dbl(a);
+            __syncwarp(quad_mask());
+            if (R.is_zero()) return dbl(x, a);
             return xyzz_t<F>::identity();
         }
         F PP, RR, ZZ12, ZZZ12;
-        mul4(Pp, Pp, R, R, a.zz, b.zz, a.zzz, b.zzz, PP, RR, ZZ12, ZZZ12);
+        mul4(x, 1, Pp, Pp, R, R, a.zz, b.zz, a.zzz, b.zzz, PP, RR, ZZ12, ZZZ12);
         F PPP, Q, ZZ3, d0;
-        mul4(Pp, PP, U1, PP, ZZ12, PP, PP, PP, PPP, Q, ZZ3, d0);
+        mul4(x, 0, Pp, PP, U1, PP, ZZ12, PP, PP, PP, PPP, Q, ZZ3, d0);
         xyzz_t<F> r;
         r.x = F::sub(F::sub(RR, PPP), F::dbl(Q));
         F T1, T2, ZZZ3;
-        mul4(R, F::sub(Q, r.x), S1, PPP, ZZZ12, PPP, PPP, PPP, T1, T2, ZZZ3, d0);
+        mul4(x, 1, R, F::sub(Q, r.x), S1, PPP, ZZZ12, PPP, PPP, PPP, T1, T2, ZZZ3, d0);
         r.y = F::sub(T1, T2);
         r.zz = ZZ3;
         r.zzz = ZZZ3;
+        __syncwarp(quad_mask());
         return r;
     }
 };

@@ -385,7 +385,7 @@ struct Fq2 {
     B2_HD static Fq2 neg(const Fq2& a) { Fq2 r; r.c0 = Fq::neg(a.c0); r.c1 = Fq::neg(a.c1); return r; }
     B2_HD static Fq2 dbl(const Fq2& a) { return add(a, a); }
     // one out-of-line unit per Fq2 product (3 inlined Fq products): 10 calls per mixed add instead of 28
-    B2_HD_NI static Fq2 mul(const Fq2& a, const Fq2& b) {
+    B2_HD_NI static Fq2 mul(const Fq2 a, const Fq2 b) {
         Fq v0 = Fq::mul(a.c0, b.c0), v1 = Fq::mul(a.c1, b.c1);
         Fq s = Fq::mul(Fq::add(a.c0, a.c1), Fq::add(b.c0, b.c1));
         Fq2 r;
@@ -393,7 +393,7 @@ struct Fq2 {
         r.c1 = Fq::sub(Fq::sub(s, v0), v1);
         return r;
     }
-    B2_HD_NI static Fq2 sqr(const Fq2& a) {
+    B2_HD_NI static Fq2 sqr(const Fq2 a) {
         Fq t = Fq::mul(Fq::add(a.c0, a.c1), Fq::sub(a.c0, a.c1));
         Fq u = Fq::mul(a.c0, a.c1);
         Fq2 r; r.c0 = t; r.c1 = Fq::dbl(u); return r;

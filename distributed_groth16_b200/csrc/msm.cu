@@ -16,6 +16,7 @@
 //                tree-combined per window in shared memory
 //   6 combine    Horner over windows (c doublings each)
 #include "common.cuh"
+#include "glv.cuh"
 
 namespace b200zk {
 
@@ -70,6 +71,43 @@ __global__ void k_msm_digits(const Fr* scalars, uint32_t n, uint32_t c, uint32_t
         }
         keys[(size_t)w * n + i] = key;
         ranks[(size_t)w * n + i] = rank;
+    }
+}
+
+// G1 only: k = k1 + k2 lambda (glv.cuh); the digits of |k1| fill windows [0, Wh), those of |k2| windows [Wh, 2 Wh)
+// over the same points -- phi is applied once to the second group's result in k_msm_combine_glv.
+__global__ void k_msm_digits_glv(const Fr* scalars, uint32_t n, uint32_t c, uint32_t Wh, uint32_t* keys, uint32_t* ranks,
+                                 uint32_t* counts) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr s = Fr::from_mont(ld16(scalars + i));
+    GlvSplit sp = glv_decompose(s.l);
+    const uint32_t B = 1u << (c - 1);
+    const uint32_t mask = (1u << c) - 1;
+    for (uint32_t h = 0; h < 2; ++h) {
+        uint32_t k[5];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) k[j] = h ? sp.k2[j] : sp.k1[j];
+        k[4] = 0;
+        const uint32_t sgn = h ? (sp.neg2 ? 1u : 0u) : (sp.neg1 ? 1u : 0u);
+        uint32_t carry = 0;
+        for (uint32_t w = 0; w < Wh; ++w) {
+            uint32_t off = w * c, limb = off >> 5, sh = off & 31;
+            uint64_t v = limb < 4 ? ((uint64_t)k[limb] | ((uint64_t)k[limb + 1] << 32)) : 0;
+            uint32_t d = ((uint32_t)(v >> sh) & mask) + carry;
+            uint32_t key = KEY_NONE, rank = 0;
+            carry = 0;
+            uint32_t neg = 0;
+            if (d > B) { d = (1u << c) - d; neg = 1; carry = 1; }
+            if (d != 0) {
+                uint32_t g = (h * Wh + w) * B + (d - 1);
+                rank = atomicAdd(counts + g, 1u);
+                key = g | ((neg ^ sgn) << 31);
+            }
+            size_t slot = (size_t)(h * Wh + w) * n + i;
+            keys[slot] = key;
+            ranks[slot] = rank;
+        }
     }
 }
 
@@ -218,8 +256,9 @@ __global__ void k_msm_task_order(const uint32_t* offsets, const uint32_t* task_o
     order[hist[len] + task_rank[t]] = t;
 }
 
+// G2 (Fq2 coordinates) needs ~2x the registers of G1: capping it at 128 spilled 1.1 KB/thread to local memory
 template <class F>
-__global__ void __launch_bounds__(128, B2_ACC_MINBLOCKS) k_msm_accumulate(const affine_t<F>* bases, const uint32_t* entries, const uint32_t* offsets,
+__global__ void __launch_bounds__(128, sizeof(F) > 32 ? 2 : B2_ACC_MINBLOCKS) k_msm_accumulate(const affine_t<F>* bases, const uint32_t* entries, const uint32_t* offsets,
                                  const uint32_t* task_off, const uint32_t* task_bucket, const uint32_t* order,
                                  uint32_t nbuckets, xyzz_t<F>* buckets, xyzz_t<F>* task_sums) {
     uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -323,18 +362,46 @@ __global__ void __launch_bounds__(THREADS) k_msm_window_sum(const xyzz_t<F>* par
     if (threadIdx.x == 0) st16(wsum + blockIdx.x, sh[0]);
 }
 
-// 6. Horner over windows: ONE warp, its 8 quads run the same chain redundantly so that the quad shuffles can use
-// the full mask (quad_ops<F, true>)
+// 6. Horner over windows: one quad; the (up to 4) independent field products of each level of a point operation
+// are computed by the 4 lanes in the same instruction stream and exchanged through shared memory (quad_ops)
 template <class F>
 __global__ void __launch_bounds__(32) k_msm_combine(const xyzz_t<F>* wsum, uint32_t W, uint32_t c, xyzz_t<F>* out) {
-    typedef quad_ops<F, true> Q;
-    if (blockIdx.x != 0) return;
+    typedef quad_ops<F, false> Q;
+    __shared__ typename Q::xch_t xch;
+    if (blockIdx.x != 0 || threadIdx.x >= 4) return;
     xyzz_t<F> total = ld16(wsum + (W - 1));
     for (int w = (int)W - 2; w >= 0; --w) {
-        for (uint32_t k = 0; k < c; ++k) total = Q::dbl(total);
-        total = Q::add(total, ld16(wsum + w));
+        for (uint32_t k = 0; k < c; ++k) total = Q::dbl(&xch, total);
+        total = Q::add(&xch, total, ld16(wsum + w));
     }
     if (threadIdx.x == 0) st16(out, total);
+}
+
+// GLV variant: quad 0 runs the Horner chain of windows [0, Wh), quad 1 that of [Wh, 2 Wh) in the same warp (half as
+// many sequential doublings); result = H0 + phi(H1), phi(X, Y, ZZ, ZZZ) = (beta X, Y, ZZ, ZZZ).
+__global__ void __launch_bounds__(32) k_msm_combine_glv(const xyzz_t<Fq>* wsum, uint32_t Wh, uint32_t c, xyzz_t<Fq>* out) {
+    typedef quad_ops<Fq, false> Q;
+    __shared__ Q::xch_t xch[2];
+    __shared__ xyzz_t<Fq> h1;
+    if (blockIdx.x != 0 || threadIdx.x >= 8) return;
+    const uint32_t half = threadIdx.x >> 2;
+    const xyzz_t<Fq>* ws = wsum + half * Wh;
+    xyzz_t<Fq> total = ld16(ws + (Wh - 1));
+    for (int w = (int)Wh - 2; w >= 0; --w) {
+        for (uint32_t k = 0; k < c; ++k) total = Q::dbl(&xch[half], total);
+        total = Q::add(&xch[half], total, ld16(ws + w));
+    }
+    if (threadIdx.x == 4) h1 = total;
+    __syncwarp(0xFFu);
+    if (half == 0) {
+        xyzz_t<Fq> p = h1;
+        Fq beta;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) beta.l[i] = GlvParams::beta(i);
+        if (!p.is_inf()) p.x = Fq::mul(p.x, beta);
+        total = Q::add(&xch[0], total, p);
+        if (threadIdx.x == 0) st16(out, total);
+    }
 }
 
 // sum `count` XYZZ points, normalise; out = affine followed by one u64 infinity flag
@@ -395,7 +462,10 @@ static int msm_dev_impl(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const vo
     }
     if (n >= (1ull << 31)) return set_error(ctx, B200ZK_ERR_ARG, "MSM length must be < 2^31");
     const unsigned c = choose_window(n);
-    const unsigned W = (255 + c - 1) / c;
+    static const bool glv_env = !(getenv("B200ZK_MSM_GLV") && getenv("B200ZK_MSM_GLV")[0] == '0');
+    const bool glv = glv_env && sizeof(F) == 32;             // G1 only (glv.cuh)
+    const unsigned Wh = (128 + c - 1) / c;                   // |k1|, |k2| < 2^127: Wh * c >= 128 leaves the carry room
+    const unsigned W = glv ? 2 * Wh : (255 + c - 1) / c;
     const uint32_t B = 1u << (c - 1);
     const uint32_t nb = W * B;
     uint32_t seg_len = B < 16 ? B : 16;
@@ -446,8 +516,10 @@ static int msm_dev_impl(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const vo
     B2_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, ((size_t)nb + 1) * 4, st));
     {
         LaunchScope ls(ctx, st, "msm_digits");
-        k_msm_digits<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const Fr*>(d_scalars), (uint32_t)n, c, W,
-                                                                    keys, ranks, counts);
+        if (glv) k_msm_digits_glv<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const Fr*>(d_scalars), (uint32_t)n, c,
+                                                                              Wh, keys, ranks, counts);
+        else k_msm_digits<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const Fr*>(d_scalars), (uint32_t)n, c, W,
+                                                                         keys, ranks, counts);
     }
     B2_TRY(check_launch(ctx, "k_msm_digits"));
     B2_TRY(exclusive_scan(ctx, st, counts, offsets, sums, nb + 1));
@@ -532,7 +604,8 @@ static int msm_dev_impl(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const vo
     B2_TRY(check_launch(ctx, "k_msm_window_sum"));
     {
         LaunchScope ls(ctx, st, "msm_combine");
-        k_msm_combine<F><<<1, 32, 0, st>>>(wsum, W, c, out);
+        if (glv) k_msm_combine_glv<<<1, 32, 0, st>>>(reinterpret_cast<const xyzz_t<Fq>*>(wsum), Wh, c, reinterpret_cast<xyzz_t<Fq>*>(out));
+        else k_msm_combine<F><<<1, 32, 0, st>>>(wsum, W, c, out);
     }
     return check_launch(ctx, "k_msm_combine");
 }

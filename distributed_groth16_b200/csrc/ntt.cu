@@ -118,6 +118,12 @@ struct PassParams {
     // w_N^(col * k1) uses (1, 0, 0) and the distributed coefficient shift w_2m^(k1 + N1 k2) uses (0, 1, N1).
     uint64_t post_b0, post_alpha, post_beta, post_gamma;
     size_t batch_stride;
+    // fused four-step exchange: the last pass stores output k of batch element (= matrix column) c straight into
+    // the row-major receive buffer of the rank that owns row k, over NVLink peer mappings (no pack / all-to-all /
+    // unpack passes): dst = peer_out[k >> log_rl] + ((k & (rl-1)) << log_cols_total) + col0 + c
+    Fr* peer_out[8];
+    uint32_t p2p, log_rl, log_cols_total;
+    uint64_t col0;
 };
 
 __global__ void __launch_bounds__(512) k_ntt_pass(PassParams p) {
@@ -195,7 +201,12 @@ __global__ void __launch_bounds__(512) k_ntt_pass(PassParams p) {
             if (ex) v = Fr::mul(v, powtab_get(p.post, ex));
         }
         if (p.apply_post_const) v = Fr::mul(v, ld_fr(p.post_const));
-        st_fr(out + oaddr, v);
+        if (p.p2p) {
+            Fr* dst = p.peer_out[oaddr >> p.log_rl] + ((oaddr & ((1ull << p.log_rl) - 1)) << p.log_cols_total) + p.col0 + blockIdx.y;
+            st_fr(dst, v);
+        } else {
+            st_fr(out + oaddr, v);
+        }
     }
 }
 
@@ -291,9 +302,11 @@ void ntt_free_plans(b200zk_ctx* ctx) {
 // Runs all passes.  pre / post may be null.  post_const: device pointer or null.
 struct PostExp { uint64_t b0, alpha, beta, gamma; };
 static const PostExp POST_PLAIN = {0, 0, 0, 1};
+struct P2PStore { Fr* peer[8]; unsigned n_peers, log_rl, log_cols_total; uint64_t col0; };
 
 static int ntt_run(b200zk_ctx* ctx, Slot& sl, NttPlan* pl, const Fr* d_in, Fr* d_out, unsigned batch,
-                   const PowTab* pre, const PowTab* post, const Fr* post_const, PostExp pe = POST_PLAIN) {
+                   const PowTab* pre, const PowTab* post, const Fr* post_const, PostExp pe = POST_PLAIN,
+                   const P2PStore* p2p = nullptr) {
     cudaStream_t st = sl.stream;
     const size_t N = (size_t)1 << pl->log_n;
     if (pl->npass == 0) {   // N == 1: X[0] = x[0] (all scale factors are 1)
@@ -327,6 +340,10 @@ static int ntt_run(b200zk_ctx* ctx, Slot& sl, NttPlan* pl, const Fr* d_in, Fr* d
         }
         if (last && post_const) { p.post_const = post_const; p.apply_post_const = 1; }
         p.batch_stride = N;
+        if (last && p2p) {
+            for (unsigned g = 0; g < 8; ++g) p.peer_out[g] = g < p2p->n_peers ? p2p->peer[g] : nullptr;
+            p.p2p = 1; p.log_rl = p2p->log_rl; p.log_cols_total = p2p->log_cols_total; p.col0 = p2p->col0;
+        }
         uint32_t RG = 1u << (p.logR + p.logG);
         uint32_t threads = RG / 2 < 32 ? 32 : RG / 2;
         size_t smem = (size_t)(2 * RG + (1u << p.logR)) * sizeof(uint4);
@@ -422,6 +439,29 @@ int ntt_batched_post_dev(b200zk_ctx* ctx, Slot& sl, const Fr* d_in, Fr* d_out, u
 int fourstep_cols_dev(b200zk_ctx* ctx, Slot& sl, const Fr* d_in, Fr* d_out, unsigned log_rows, unsigned log_cols_local,
                       unsigned log_n, uint64_t global_col0, bool inverse) {
     return ntt_batched_post_dev(ctx, sl, d_in, d_out, log_rows, 1u << log_cols_local, inverse, log_n, false, global_col0, 1, 0, 0);
+}
+
+// Column step of the four-step NTT fused with the exchange: the transformed, twiddled columns are written directly
+// into the peers' row-major receive buffers (P2P stores over NVLink) -- the compute kernel IS the all-to-all.
+int fourstep_cols_p2p_dev(b200zk_ctx* ctx, Slot& sl, const Fr* d_in, void* const* peer_out, unsigned n_peers, unsigned log_rows,
+                          unsigned log_cols_local, unsigned log_n, uint64_t global_col0, bool inverse) {
+    if (n_peers == 0 || n_peers > 8 || (n_peers & (n_peers - 1))) return set_error(ctx, B200ZK_ERR_ARG, "peer count must be 1, 2, 4 or 8");
+    if (log_rows == 0 || log_rows > 28 || log_n > 28) return set_error(ctx, B200ZK_ERR_DOMAIN, "bad four-step geometry");
+    unsigned log_p = ceil_log2(n_peers);
+    if (log_rows < log_p) return set_error(ctx, B200ZK_ERR_ARG, "fewer rows than peers");
+    NttPlan *pl, *base_plan;
+    B2_TRY(get_plan(ctx, sl.stream, log_rows, inverse, &pl));
+    B2_TRY(get_plan(ctx, sl.stream, log_n, inverse, &base_plan));
+    P2PStore ps;
+    for (unsigned g = 0; g < 8; ++g) ps.peer[g] = g < n_peers ? reinterpret_cast<Fr*>(peer_out[g]) : nullptr;
+    ps.n_peers = n_peers;
+    ps.log_rl = log_rows - log_p;
+    ps.log_cols_total = log_n - log_rows;
+    ps.col0 = global_col0;
+    PostExp pe = {global_col0, 1, 0, 0};
+    // d_out is only used by the earlier passes' scratch chain; the last pass stores remotely
+    Fr* dummy_out = reinterpret_cast<Fr*>(peer_out[0]);
+    return ntt_run(ctx, sl, pl, d_in, dummy_out, 1u << log_cols_local, nullptr, &base_plan->tw, inverse ? pl->consts + 1 : nullptr, pe, &ps);
 }
 
 // out[i] = a[i]*b[i] - c[i]   (ext_wit.rs:88-92 on device-resident vectors)

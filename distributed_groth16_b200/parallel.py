@@ -220,3 +220,116 @@ def sharded_prove(net, spk: ShardedProvingKey, z_shard, z_aux_shard, a, b, c, lo
                                               c_vp(base + 384) if need_b1 else None, c_vp(r.ctypes.data), c_vp(s.ctypes.data),
                                               0, out))
     return bytes(out)
+
+
+# ---------------------------------------------------------------------------------------------
+# fused compute + exchange: the four-step NTT with the all-to-all folded into the column kernel
+# ---------------------------------------------------------------------------------------------
+class P2PExchange:
+    """Peer-mapped receive buffers for `sharded_ntt_p2p`.
+
+    Every rank allocates two row-major receive buffers with b200zk_peer_alloc (cudaMalloc + CUDA IPC), the 64-byte
+    handles are all-gathered once, and every rank maps every peer's buffers (NVLink peer access).  The column kernel
+    of a transform then stores its outputs directly into the owners' buffers; two buffers alternate so that a rank
+    still reading transform t's rows is never overwritten by a faster peer already in transform t+1 (the barrier of
+    transform t+1 orders transform t+2's writes after those reads)."""
+
+    def __init__(self, net, n_elems: int, group=None):
+        import torch
+        import torch.distributed as dist
+        self.net, self.group = net, group
+        self.world, self.rank = _world(group)
+        self.n_elems = n_elems
+        self.bytes = n_elems * 32
+        lib, h = net._lib, net._h
+        self.local = []
+        handles = []
+        for _ in range(2):
+            ptr = c_vp()
+            hb = (ctypes.c_uint8 * 64)()
+            net.check(lib.b200zk_peer_alloc(h, self.bytes, ctypes.byref(ptr), hb))
+            self.local.append(ptr.value)
+            handles.append(bytes(hb))
+        self.peers = [[None] * self.world for _ in range(2)]
+        if self.world > 1:
+            dev = torch.device("cuda", net.device)
+            mine = torch.tensor(list(handles[0] + handles[1]), dtype=torch.uint8, device=dev)
+            allh = torch.empty((self.world, 128), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, mine.reshape(1, -1), group=group)
+            allh = allh.cpu().numpy()
+            for g in range(self.world):
+                for b in range(2):
+                    if g == self.rank:
+                        self.peers[b][g] = self.local[b]
+                    else:
+                        raw = (ctypes.c_uint8 * 64).from_buffer_copy(allh[g, 64 * b:64 * (b + 1)].tobytes())
+                        ptr = c_vp()
+                        net.check(lib.b200zk_peer_open(h, raw, ctypes.byref(ptr)))
+                        self.peers[b][g] = ptr.value
+        else:
+            for b in range(2):
+                self.peers[b][0] = self.local[b]
+        self.turn = 0
+        self._flag = None
+
+    def recv_tensor(self, b: int, shape):
+        """torch view of local receive buffer b (no copy)."""
+        import torch
+
+        class _Holder:
+            pass
+        hold = _Holder()
+        n = int(np.prod(shape))
+        hold.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (self.local[b], False), "version": 2}
+        return torch.as_tensor(hold, device=torch.device("cuda", self.net.device)).reshape(shape)
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
+            if self._flag is None:
+                self._flag = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", self.net.device))
+            dist.all_reduce(self._flag, group=self.group)      # stream-ordered: all ranks' column kernels have completed
+
+    def close(self):
+        lib, h = self.net._lib, self.net._h
+        for b in range(2):
+            for g in range(self.world):
+                if g != self.rank and self.peers[b][g]:
+                    lib.b200zk_peer_close(h, c_vp(self.peers[b][g]))
+            lib.b200zk_peer_free(h, c_vp(self.local[b]))
+
+
+def sharded_ntt_p2p(net, xch: P2PExchange, local, log_rows: int, log_cols: int, inverse: bool = False,
+                    shift_log_m: int | None = None):
+    """Same transform and layouts as `sharded_ntt`, with the exchange fused into the column kernel: no pack,
+    no NCCL all-to-all, no unpack -- the kernel's stores are the transfer (b200zk_ntt_fr_fourstep_cols_p2p_dev)."""
+    world, rank = xch.world, xch.rank
+    rows, cols = 1 << log_rows, 1 << log_cols
+    cg, rl = cols // world, rows // world
+    assert tuple(local.shape) == (cg, rows, 4) and rl * cols <= xch.n_elems
+    b = xch.turn
+    xch.turn ^= 1
+    ptrs = (c_vp * world)(*[c_vp(p) for p in xch.peers[b]])
+    net.check(net._lib.b200zk_ntt_fr_fourstep_cols_p2p_dev(net._h, 0, c_vp(local.data_ptr()), ptrs, world, log_rows,
+                                                           cg.bit_length() - 1, log_rows + log_cols,
+                                                           ctypes.c_uint64(rank * cg), int(inverse)))
+    xch.barrier()
+    rows_in = xch.recv_tensor(b, (rl * cols, 4))
+    be = GpuBackend(net)
+    if shift_log_m is None:
+        out = be.batched_ntt_post(rows_in, log_cols, rl, inverse, post=False)
+    else:
+        out = be.batched_ntt_post(rows_in, log_cols, rl, inverse, log_base=shift_log_m + 1, shift=True, b0=rank * rl,
+                                  alpha=0, beta=1, gamma=rows)
+    return out.reshape(rl, cols, 4)
+
+
+def sharded_h_p2p(net, xch: P2PExchange, a, b, c, log_m: int):
+    """`sharded_h` on the fused transforms."""
+    log_rows, log_cols = split_log(log_m)
+    ev = []
+    for v in (a, b, c):
+        coef = sharded_ntt_p2p(net, xch, v, log_rows, log_cols, inverse=True, shift_log_m=log_m)
+        ev.append(sharded_ntt_p2p(net, xch, coef, log_cols, log_rows, inverse=False))
+    return GpuBackend(net).mul_sub(ev[0], ev[1], ev[2])

@@ -92,6 +92,21 @@ int b200zk_ntt_fr_dev(b200zk_ctx* ctx, int stream, const void* d_in, void* d_out
 int b200zk_ntt_fr_fourstep_cols_dev(b200zk_ctx* ctx, int stream, const void* d_in, void* d_out, unsigned log_rows,
                                     unsigned log_cols_local, unsigned log_n, uint64_t global_col0, int inverse);
 
+/* Fused compute + exchange (the B200-native four-step): same column transform, but the last pass stores every
+ * output element directly into the receive buffer of the rank that owns its row, through NVLink peer mappings --
+ * no pack / NCCL all-to-all / unpack passes.  peer_out[g]: device pointer (valid in THIS process, see
+ * b200zk_peer_open) to rank g's row-major [rows / n_peers][cols] receive buffer.  The caller orders the row step
+ * after all ranks' column steps with a stream-ordered barrier (parallel.sharded_ntt_p2p uses a 1-element all-reduce). */
+int b200zk_ntt_fr_fourstep_cols_p2p_dev(b200zk_ctx* ctx, int stream, const void* d_in, void* const* peer_out,
+                                        unsigned n_peers, unsigned log_rows, unsigned log_cols_local, unsigned log_n,
+                                        uint64_t global_col0, int inverse);
+/* Peer-visible device memory (cudaMalloc + CUDA IPC): allocate locally and export a 64-byte handle; open a peer's
+ * handle to obtain a pointer usable by this process's kernels. */
+int b200zk_peer_alloc(b200zk_ctx* ctx, size_t bytes, void** d_ptr, uint8_t handle_out[64]);
+int b200zk_peer_open(b200zk_ctx* ctx, const uint8_t handle[64], void** d_ptr);
+int b200zk_peer_close(b200zk_ctx* ctx, void* d_ptr);
+int b200zk_peer_free(b200zk_ctx* ctx, void* d_ptr);
+
 /* Generalised building block: `batch` contiguous transforms of size 2^log_t; output k of transform b is
  * multiplied by base^((b + b0)(alpha k + beta) + gamma k) where base = w_{2^log_base} (direction of the
  * transform) or, with base_is_shift, the forward root w_{2^log_base} used by the h coefficient shift.

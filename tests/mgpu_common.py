@@ -117,3 +117,27 @@ def _cols_g1(pts, ncols, world, rank):
     cg = ncols // world
     mview = pts.reshape(n // ncols, ncols, 8)
     return np.ascontiguousarray(mview[:, rank * cg:(rank + 1) * cg].transpose(1, 0, 2))
+
+
+def check_p2p(net, to_dev, rank, world, log_m=10):
+    """Fused four-step (P2P stores) == NCCL four-step == oracle."""
+    from oracle import cref
+    m = 1 << log_m
+    log_rows, log_cols = par.split_log(log_m)
+    rows, cols = 1 << log_rows, 1 << log_cols
+    xch = par.P2PExchange(net, max(rows, cols) * max(rows, cols) // world)
+    ok = True
+    x = cref.fr_generate(0xF00D, m)
+    loc = to_dev(par.to_column_layout(x, cols, world, rank))
+    for inverse in (False, True):
+        out = par.sharded_ntt_p2p(net, xch, loc, log_rows, log_cols, inverse=inverse)
+        exp = par.to_column_layout(cref.ntt(x, inverse=inverse), rows, world, rank)
+        ok = ok and bool((out.cpu().numpy().view(np.uint64) == exp).all())
+    a, b, c = (cref.fr_generate(sd, m) for sd in (21, 22, 23))
+    la, lb, lc = (to_dev(par.to_column_layout(v, cols, world, rank)) for v in (a, b, c))
+    h = par.sharded_h_p2p(net, xch, la, lb, lc, log_m)
+    ok = ok and bool((h.cpu().numpy().view(np.uint64) == par.to_column_layout(cref.h_circom(a, b, c), cols, world, rank)).all())
+    import torch
+    torch.cuda.synchronize()
+    xch.close()
+    return ok

@@ -29,6 +29,8 @@ def main():
         res.update({"%s@2^%d" % (k, log_m): v for k, v in r.items()})
     for log_m, rs in ((8, (0, 0)), (12, (5, 7))):
         res["sharded_prove@2^%d" % log_m] = bool(mc.check_sharded_prove(net, to_dev, rank, world, log_m=log_m, rs=rs))
+    for log_m in (6, 13, 16):
+        res["p2p_fused_ntt@2^%d" % log_m] = bool(mc.check_p2p(net, to_dev, rank, world, log_m=log_m))
     flat = torch.tensor([int(all(res.values()))], device=dev)
     dist.all_reduce(flat, op=dist.ReduceOp.MIN)
     if rank == 0:

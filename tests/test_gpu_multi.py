@@ -22,6 +22,8 @@ def test_sharded_paths_world1(net):
     for log_m in (2, 5, 10, 15):
         res = mc.check_all(par.GpuBackend(net), to_dev, 0, 1, log_m=log_m, msm_n=256)
         assert all(res.values()), (log_m, res)
+    for log_m in (3, 8, 12):
+        assert mc.check_p2p(net, to_dev, 0, 1, log_m=log_m)
     for log_m, rs in ((4, (0, 0)), (9, (3, 4))):
         assert mc.check_sharded_prove(net, to_dev, 0, 1, log_m=log_m, rs=rs)
 
