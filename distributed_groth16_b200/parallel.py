@@ -179,22 +179,26 @@ class ShardedProvingKey:
                                          1, vk_points)
 
 
-def sharded_prove(net, spk: ShardedProvingKey, z_shard, z_aux_shard, a, b, c, log_m: int, r=None, s=None, group=None):
+def sharded_prove(net, spk: ShardedProvingKey, z_shard, z_aux_shard, a, b, c, log_m: int, r=None, s=None, group=None,
+                  xch=None):
     """Groth16 proof with every vector sharded over the ranks of `group`.
 
     z_shard: this rank's rows of the full assignment (aligned with spk.a_query); z_aux_shard: its rows of
     z[n_inputs:] (aligned with spk.l_query); a, b, c: QAP evaluations in the column layout (see sharded_ntt).
+    xch: a P2PExchange -> the h pipeline uses the fused NTT + NVLink exchange instead of NCCL all-to-all.
     Every rank returns the same 128 bytes."""
     import torch
     import torch.distributed as dist
-    from ._native import c_vp
     world, rank = _world(group)
     be = GpuBackend(net)
     zero = np.zeros(4, dtype=np.uint64)
     r = zero if r is None else np.ascontiguousarray(r, dtype=np.uint64)
     s = zero if s is None else np.ascontiguousarray(s, dtype=np.uint64)
     need_b1 = bool(r.any())
-    h = sharded_h(be, a, b, c, log_m, group=group).reshape(-1, 4)
+    if xch is not None:          # fused four-step: NTT column kernels store straight into the peers' buffers
+        h = sharded_h_p2p(net, xch, a, b, c, log_m).reshape(-1, 4)
+    else:
+        h = sharded_h(be, a, b, c, log_m, group=group).reshape(-1, 4)
     dev = z_shard.device
     # slots: 0 A(G1) 1 L 2 H 3 B1 (each 16 words) then B2 (32 words)
     parts = torch.zeros(4 * 16 + 32, dtype=torch.int64, device=dev)

@@ -53,21 +53,45 @@ def main():
                                 cols_layout(hq, cols, world, rank), n_inputs, vk)
     z_sh, zaux_sh = z[sl].contiguous(), z[n_inputs:][sla].contiguous()
     la, lb, lc = (cols_layout(v, cols, world, rank) for v in (a, b, c))
-    times = []
-    proof = None
-    for it in range(5):
+    rows = 1 << log_rows
+    xch = par.P2PExchange(net, rows * rows // world)
+    out = {"config": "Groth16 prove 2^%d synthetic, sharded x%d" % (log_m, world), "log_m": log_m, "world": world}
+    proofs = {}
+    for mode, x in (("nccl_all_to_all", None), ("p2p_fused", xch)):
+        times = []
+        for it in range(5):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            proof = par.sharded_prove(net, spk, z_sh, zaux_sh, la, lb, lc, log_m, xch=x)
+            torch.cuda.synchronize()
+            times.append((time.perf_counter() - t0) * 1e3)
+        t = torch.tensor(sorted(times[2:])[1], device="cuda", dtype=torch.float64)
         if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        proof = par.sharded_prove(net, spk, z_sh, zaux_sh, la, lb, lc, log_m)
-        torch.cuda.synchronize()
-        times.append((time.perf_counter() - t0) * 1e3)
-    t = torch.tensor(sorted(times[2:])[1], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    out = {"config": "Groth16 prove 2^%d synthetic, sharded x%d" % (log_m, world), "log_m": log_m, "world": world,
-           "ms_prove_sharded": float(t), "runs_ms_rank0": times}
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["ms_prove_sharded_" + mode] = float(t)
+        proofs[mode] = proof
+        # the h pipeline alone (6 transforms + pointwise), same two exchange mechanisms
+        ht = []
+        be = par.GpuBackend(net)
+        for it in range(4):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            if x is None:
+                par.sharded_h(be, la, lb, lc, log_m)
+            else:
+                par.sharded_h_p2p(net, x, la, lb, lc, log_m)
+            torch.cuda.synchronize()
+            ht.append((time.perf_counter() - t0) * 1e3)
+        t = torch.tensor(sorted(ht[1:])[1], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["ms_h_sharded_" + mode] = float(t)
+    assert proofs["nccl_all_to_all"] == proofs["p2p_fused"]
+    proof = proofs["p2p_fused"]
     if rank == 0:
         pk = ProvingKey.from_device(net, aq, b1, b2, lq, hq, n_inputs, vk)
         ts = []
