@@ -466,6 +466,7 @@ static int msm_dev_impl(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const vo
     const bool glv = glv_env && sizeof(F) == 32;             // G1 only (glv.cuh)
     const unsigned Wh = (128 + c - 1) / c;                   // |k1|, |k2| < 2^127: Wh * c >= 128 leaves the carry room
     const unsigned W = glv ? 2 * Wh : (255 + c - 1) / c;
+    if ((uint64_t)W * n >= (1ull << 32)) return set_error(ctx, B200ZK_ERR_ARG, "MSM too large for 32-bit bucket offsets (W * n >= 2^32)");
     const uint32_t B = 1u << (c - 1);
     const uint32_t nb = W * B;
     uint32_t seg_len = B < 16 ? B : 16;

@@ -35,6 +35,8 @@ struct NttPlan {
     Fr* twR[8];          // per pass: w_R^i, i < R/2
     Fr* consts = nullptr;  // [0] w_N (direction applied) [1] n^-1 [2] coset generator (g or g^-1) [3] w_2N (forward)
     PowTab tw;           // powers of consts[0]
+    PowTab tw_pass[8];   // middle passes: single-level table of w_N^(L i), i < N/L (one product less per element)
+    bool has_tw_pass[8];
     PowTab coset;        // powers of consts[2]   (lazy)
     PowTab shift;        // powers of consts[3]   (lazy; used by h)
     std::vector<void*> allocs;
@@ -107,6 +109,7 @@ struct PassParams {
     const Fr* in;
     Fr* out;
     uint32_t log_n, logL, logR, logM, logG;
+    uint32_t tw_shift;           // exponent of the inter-pass twiddle = (n'' k_s) << tw_shift
     const Fr* twR;
     PowTab tw;
     PowTab pre;
@@ -192,7 +195,7 @@ __global__ void __launch_bounds__(512) k_ntt_pass(PassParams p) {
         Fr v;
         v.l[0] = a.x; v.l[1] = a.y; v.l[2] = a.z; v.l[3] = a.w; v.l[4] = bq.x; v.l[5] = bq.y; v.l[6] = bq.z; v.l[7] = bq.w;
         if (p.apply_tw) {
-            uint64_t ex = (n2 * ks) << p.logL;
+            uint64_t ex = (n2 * ks) << p.tw_shift;
             if (ex) v = Fr::mul(v, powtab_get(p.tw, ex));
         }
         uint64_t oaddr = ((j + ((uint64_t)ks << p.logL)) << p.logM) + n2;
@@ -273,6 +276,27 @@ static int get_plan(b200zk_ctx* ctx, cudaStream_t st, unsigned log_n, bool inver
     }
     B2_TRY(check_launch(ctx, "k_build_pow(twR)"));
     B2_TRY(build_powtab(ctx, st, pl, pl->consts, log_n, &pl->tw));
+    {
+        unsigned logL = 0;
+        for (unsigned i = 0; i < pl->npass; ++i) {
+            pl->has_tw_pass[i] = false;
+            unsigned range = log_n - logL;                      // exponents n'' k_s < N / L
+            if (i > 0 && i + 1 < pl->npass && range <= 16) {
+                Fr* t = nullptr;
+                B2_CUDA_OK(ctx, cudaMalloc(&t, sizeof(Fr) << range));
+                pl->allocs.push_back(t);
+                {
+                    LaunchScope ls(ctx, st, "ntt_build_tables");
+                    uint32_t cnt = 1u << range;
+                    k_build_pow<<<(cnt + 127) / 128, 128, 0, st>>>(pl->consts, t, cnt, logL);
+                }
+                B2_TRY(check_launch(ctx, "k_build_pow(tw_pass)"));
+                pl->tw_pass[i].lo = t; pl->tw_pass[i].hi = t; pl->tw_pass[i].lo_bits = range;
+                pl->has_tw_pass[i] = true;
+            }
+            logL += pl->logR[i];
+        }
+    }
     // tables are built on `st`; other slots may use the plan later, so finish construction here
     B2_CUDA_OK(ctx, cudaStreamSynchronize(st));
     ctx->plans[key] = pl;
@@ -332,6 +356,8 @@ static int ntt_run(b200zk_ctx* ctx, Slot& sl, NttPlan* pl, const Fr* d_in, Fr* d
         p.logG = log_cols < LOG_G ? log_cols : LOG_G;
         p.twR = pl->twR[i];
         p.tw = pl->tw;
+        p.tw_shift = logL;
+        if (pl->has_tw_pass[i]) { p.tw = pl->tw_pass[i]; p.tw_shift = 0; }
         p.apply_tw = last ? 0 : 1;
         if (i == 0 && pre) { p.pre = *pre; p.apply_pre = 1; }
         if (last && post) {

@@ -117,3 +117,26 @@ def test_config2_g1_2_20_device_resident(net, cref):
     from oracle import layout
     exp_sum, _ = cref.msm_g1(both, layout.fr_to_arr([1, 1]))
     assert (lhs.limbs == exp_sum).all()
+
+
+def test_larger_sizes_2_22_vs_oracle_and_2_24_linearity(net, cref):
+    """Sizes above the benchmark point (BASELINE config 2 lists 2^22..2^26): 2^22 against the CPU twin; 2^24 through a
+    size-independent property: MSM(P, s) + MSM(P, t) == MSM(P, s + t)."""
+    import torch
+    from oracle import layout
+    n = 1 << 22
+    bases = net.generate_g1(0xB2000022, n)
+    scalars = net.generate_fr(0xB2000022, n)
+    got = d_msm(bases, scalars, None, net)
+    exp, inf = cref.msm_g1(bases.cpu().numpy().view(np.uint64), scalars.cpu().numpy().view(np.uint64))
+    assert not inf and (got.limbs == exp).all()
+    del bases, scalars
+    n = 1 << 24
+    bases = net.generate_g1(0xB2000024, n)
+    s = net.generate_fr(1, n)
+    t = net.generate_fr(2, n)
+    st = torch.from_numpy(net.field_op(1, 1, s.cpu().numpy().view(np.uint64), t.cpu().numpy().view(np.uint64)).view(np.int64)).to(bases.device)
+    a, b, c = d_msm(bases, s, None, net), d_msm(bases, t, None, net), d_msm(bases, st, None, net)
+    both = np.stack([a.limbs, b.limbs])
+    exp_sum, _ = cref.msm_g1(both, layout.fr_to_arr([1, 1]))
+    assert (c.limbs == exp_sum).all() and not c.infinity

@@ -94,3 +94,17 @@ def test_config3_2_22_vs_oracle(net, cref):
     assert (net.ntt(x) == cref.ntt(x)).all()
     assert (net.ntt(x, inverse=True) == cref.ntt(x, inverse=True)).all()
     assert (net.ntt(x, coset=True) == cref.ntt(x, coset=True)).all()
+
+
+def test_roundtrip_2_24_and_2_26_device_resident(net):
+    """Largest sizes BASELINE lists (2^26 elements = 2 GiB per vector): iNTT(NTT(x)) == x."""
+    import torch
+    for log_n in (24, 26):
+        x = net.generate_fr(0xB2000000 + log_n, 1 << log_n)
+        net.use_torch_stream(0)
+        y = net.ntt_dev(x)
+        z = net.ntt_dev(y, inverse=True)
+        torch.cuda.synchronize()
+        assert torch.equal(x, z) and not torch.equal(x[:1024], y[:1024])
+        del x, y, z
+        torch.cuda.empty_cache()
