@@ -9,6 +9,9 @@ reference's tests hold), never source:
                               - r1cs / zkey header primes (BN254 check, r1cs_reader.rs:180-188)
   complex_circuit.zkey.pk.npz the proving key of ark-circom/test-vectors/complex-circuit/*.zkey as limb arrays
                               (+ QAP matrices in COO form) -- fixture F1 of SURVEY 8c
+  sha256_circuit.npz          fixture F2: fixtures/sha256/sha256.r1cs as COO matrices + the witness for {a: 1, b: 2}
+                              computed by running fixtures/sha256/sha256_js/sha256.wasm under oracle/wasm_witness.py
+                              (public output == the KAT of groth16/examples/sha256.rs:231-233; all 30 134 constraints hold)
   complex_circuit_proof.json  the oracle's proof for witness a = 3 on that key (r = s = 0 and r, s != 0),
                               both verified against the zkey's own vk with the oracle pairing
 """
@@ -24,6 +27,21 @@ sys.path.insert(0, os.path.join(HERE, "..", ".."))
 from oracle import bn254 as o, layout  # noqa: E402
 
 REF = "/root/reference"
+
+
+def make_sha256_fixture(g):
+    from oracle import wasm_witness
+    from distributed_groth16_b200 import formats
+    r1 = formats.read_r1cs(open(REF + "/fixtures/sha256/sha256.r1cs", "rb").read())
+    w, prime = wasm_witness.calculate_witness(open(REF + "/fixtures/sha256/sha256_js/sha256.wasm", "rb").read(),
+                                              {"a": 1, "b": 2})          # zk-cli/test-circuits/sha256/input.json
+    assert prime == o.R and len(w) == r1.n_wires == 29823
+    assert w[1] == int(g["sha256_public_input"])                        # groth16/examples/sha256.rs:231-233
+    wl = np.array([[(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)] for v in w], dtype=np.uint64)
+    np.savez_compressed(os.path.join(HERE, "sha256_circuit.npz"), witness=wl,
+                        dims=np.array([r1.n_wires, r1.n_pub_out + r1.n_pub_in, r1.n_constraints], dtype=np.uint64),
+                        a_rows=r1.rows[0], a_cols=r1.cols[0], a_vals=r1.vals[0], b_rows=r1.rows[1], b_cols=r1.cols[1],
+                        b_vals=r1.vals[1], c_rows=r1.rows[2], c_cols=r1.cols[2], c_vals=r1.vals[2])
 
 
 def main():
@@ -92,6 +110,7 @@ def main():
         out[name] = dict(r=r, s=s, proof_hex=o.proof_compress(A, B, C).hex())
     out["public_input"] = str(z[1])
     json.dump(out, open(os.path.join(HERE, "complex_circuit_proof.json"), "w"), indent=1)
+    make_sha256_fixture(g)
     print("golden files written")
 
 

@@ -153,3 +153,47 @@ def test_qap_matvec_and_prove_from_zkey_wtns_bytes(net):
     assert proof.hex() == exp["r0s0"]["proof_hex"]
     assert int.from_bytes(public[0].tobytes(), "little") == int(exp["public_input"])
     pk.free()
+
+
+def test_config4_sha256_circuit_shape_qap_h_and_prove(net, cref):
+    """BASELINE config 4 (fixture F2): the reference's sha256 circuit (m = 2^15, MSM sizes 29 822 / 29 821 / 32 768) with
+    its real witness (29 821 of 29 823 entries are 0 or 1 -- the giant-bucket case).  qap() and h are checked against the
+    oracle on the real matrices; the proving key of the reference run is not reproducible here (StdRng([42;32]) setup,
+    SURVEY 8c), so the prover runs on a dummy CRS of exactly these sizes and must match the CPU twin byte for byte."""
+    import os
+    from oracle import bn254 as o, layout
+    from distributed_groth16_b200.groth16 import circom, qap as qapmod
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sha256_circuit.npz"))
+    n_wires, n_pub, n_cons = (int(x) for x in d["dims"])
+    n_inputs = n_pub + 1
+    z = net.fr_convert(net.to_device(d["witness"]), to_mont=True)
+    mats = qapmod.ConstraintMatrices(net, n_inputs, n_cons, (d["a_rows"], d["a_cols"], d["a_vals"]),
+                                     (d["b_rows"], d["b_cols"], d["b_vals"]), values_montgomery_depth=-1)
+    q = qapmod.qap(mats, z, net)
+    m = q.domain.size()
+    assert m == 1 << 15
+    w = [int.from_bytes(r.tobytes(), "little") for r in d["witness"]]
+
+    def rows(k):
+        vals = [int.from_bytes(r.tobytes(), "little") for r in d[k + "_vals"]]
+        out = [[] for _ in range(n_cons)]
+        for r_, c_, x in zip(d[k + "_rows"], d[k + "_cols"], vals):
+            out[int(r_)].append((x, int(c_)))
+        return out
+
+    ea, eb, ec = o.qap(rows("a"), rows("b"), n_inputs, n_cons, w)
+    a_h, b_h, c_h = (t.cpu().numpy().view(np.uint64) for t in (q.a, q.b, q.c))
+    assert (a_h == layout.fr_to_arr(ea)).all() and (b_h == layout.fr_to_arr(eb)).all() and (c_h == layout.fr_to_arr(ec)).all()
+    hh = cref.h_circom(a_h, b_h, c_h)
+    assert (net.h_circom(a_h, b_h, c_h) == hh).all()
+    aq, b1, lq, hq = cref.g1_generate(41, n_wires), cref.g1_generate(42, n_wires), cref.g1_generate(44, n_wires - n_inputs), cref.g1_generate(45, m)
+    b2 = cref.g2_generate(43, n_wires)
+    vk1, vk2 = cref.g1_generate(46, 3), cref.g2_generate(47, 2)
+    vk = np.concatenate([vk1.reshape(-1), vk2.reshape(-1)])
+    zero = np.zeros(4, dtype=np.uint64)
+    z_h = z.cpu().numpy().view(np.uint64)
+    exp = cref.groth16_prove(aq, b1, b2, lq, hq, vk, n_inputs, z_h, hh, zero, zero, mirror_bg1=True)
+    pk = ProvingKey(net, aq, b1, b2, lq, hq, n_inputs, vk1[0], vk1[1], vk1[2], vk2[0], vk2[1])
+    got = circom.prove_from_matrices(pk, mats, z, mirror_reference_bg1=True)
+    assert got == exp
+    pk.free()

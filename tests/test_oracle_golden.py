@@ -103,3 +103,22 @@ def test_f1_real_zkey_proof_reproduced_by_cpu_twin_and_verifies(cref):
     A, B, C = o.proof_decompress(bytes.fromhex(exp["r0s0"]["proof_hex"]))
     vk1, vk2 = layout.arr_to_g1(d["vk_g1"]), layout.arr_to_g2(d["vk_g2"])
     assert o.groth16_verify(vk1[0], vk2[0], vk2[2], vk2[1], layout.arr_to_g1(d["ic"]), [z[1]], A, B, C)
+
+
+def test_f2_sha256_witness_fixture_satisfies_the_r1cs_and_the_reference_kat():
+    """Fixture F2: witness of fixtures/sha256 for {a: 1, b: 2} (computed by oracle/wasm_witness.py from the reference's
+    own sha256.wasm).  witness[1] must equal the public output asserted in groth16/examples/sha256.rs:231-233 and every
+    constraint of sha256.r1cs must hold."""
+    d = np.load(os.path.join(G, "sha256_circuit.npz"))
+    n_wires, n_pub, n_cons = (int(x) for x in d["dims"])
+    assert (n_wires, n_pub, n_cons) == (29823, 1, 30134)                      # SURVEY 8a sizes
+    w = [int.from_bytes(r.tobytes(), "little") for r in d["witness"]]
+    assert w[0] == 1 and w[1] == int(gold["sha256_public_input"])
+    acc = {}
+    for k in "abc":
+        vals = [int.from_bytes(r.tobytes(), "little") for r in d[k + "_vals"]]
+        v = [0] * n_cons
+        for r_, c_, x in zip(d[k + "_rows"], d[k + "_cols"], vals):
+            v[int(r_)] = (v[int(r_)] + x * w[int(c_)]) % o.R
+        acc[k] = v
+    assert all(x * y % o.R == z for x, y, z in zip(acc["a"], acc["b"], acc["c"]))
