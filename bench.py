@@ -256,6 +256,7 @@ def main():
     launches = net.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     ms_step = sum(times) / len(times)
+    ms_step_sorted = sorted(times)
 
     for _ in range(2):
         step_e2e()
@@ -321,7 +322,8 @@ def main():
     kernel_ms = {k: round(v["ms"] / 5.0, 4) for k, v in rep.items()}
     out = {
         "metric": METRIC, "value": world * n / ms_step / 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": warm, "ms_per_step": ms_step, "ms_per_step_median": ms_step_sorted[len(ms_step_sorted) // 2],
+        "ms_per_step_min": ms_step_sorted[0], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32x8 Montgomery (256-bit modular integers)", "data": "synthetic",
         "config": {"workload": "BN254 G1 Pippenger MSM 2^%d random scalar/point pairs per GPU" % LOG_N,
                    "pairs_per_gpu": n, "l2": "256 MiB flush write between timed iterations; inputs+workspace > L2",

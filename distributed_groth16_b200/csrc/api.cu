@@ -57,6 +57,8 @@ void b200zk_ctx_destroy(b200zk_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     ntt_free_plans(ctx);
+    if (ctx->fb_table_g1) cudaFree(ctx->fb_table_g1);
+    if (ctx->fb_table_g2) cudaFree(ctx->fb_table_g2);
     for (int i = 0; i < 3; ++i) {
         Slot& s = ctx->slots[i];
         s.ws_msm.release(); s.ws_ntt.release(); s.io_a.release(); s.io_b.release(); s.small.release();
@@ -138,7 +140,7 @@ int b200zk_profile_json(b200zk_ctx* ctx, char* buf, size_t buf_len) {
     return B200ZK_OK;
 }
 
-uint64_t b200zk_launch_count(const b200zk_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t b200zk_launch_count(const b200zk_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
 
 }  // extern "C"
 
@@ -459,6 +461,35 @@ int b200zk_groth16_assemble_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const void
     Slot& sl = ctx->slots[0];
     std::lock_guard<std::mutex> g(sl.mu);
     return assemble_dev(ctx, sl, pk, d_msm_a, d_msm_b2, d_msm_l, d_msm_h, d_msm_b1, r, s, include_zero_terms, proof_out);
+}
+
+// ---- setup building blocks -----------------------------------------------------------------------
+int b200zk_fixed_base_mul_dev(b200zk_ctx* ctx, int g2, const void* d_scalars, size_t n, void* d_out) {
+    if (!ctx || (n && (!d_scalars || !d_out))) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[0];
+    std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    return fixed_base_mul_dev(ctx, sl, g2, d_scalars, n, d_out);
+}
+int b200zk_fr_powers_dev(b200zk_ctx* ctx, const uint64_t base[4], const uint64_t scale[4], size_t n, void* d_out) {
+    if (!ctx || !base || !scale || (n && !d_out)) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[0];
+    std::lock_guard<std::mutex> g(sl.mu);
+    return fr_powers_dev(ctx, sl, base, scale, n, d_out);
+}
+int b200zk_fr_spmv_dev(b200zk_ctx* ctx, const void* d_ptr, const void* d_idx, const void* d_val, const void* d_x, size_t n_rows,
+                       void* d_out) {
+    if (!ctx || !d_ptr || !d_x || (n_rows && !d_out)) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[0];
+    std::lock_guard<std::mutex> g(sl.mu);
+    return spmv_dev(ctx, sl, d_ptr, d_idx, d_val, d_x, n_rows, d_out);
+}
+int b200zk_fr_lincomb_dev(b200zk_ctx* ctx, const void* d_a, const void* d_b, const void* d_c, const uint64_t s[16], size_t n,
+                          void* d_out) {
+    if (!ctx || !s || (n && (!d_a || !d_b || !d_c || !d_out))) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[0];
+    std::lock_guard<std::mutex> g(sl.mu);
+    return fr_lincomb_dev(ctx, sl, d_a, d_b, d_c, s, n, d_out);
 }
 
 // ---- generators / self-test --------------------------------------------------------------------

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
@@ -65,10 +66,11 @@ struct b200zk_ctx {
     std::mutex prof_mu;
     std::vector<b200zk::ProfEntry> prof_pending;
     std::map<std::string, std::pair<uint64_t, double>> prof_acc;   // name -> (launches, ms)
-    uint64_t launches = 0;
+    std::atomic<uint64_t> launches{0};     // kernels launched (slots may be driven from different host threads)
     // NTT plans keyed by (log_n << 1 | inverse)
     std::mutex plan_mu;
     std::map<uint32_t, b200zk::NttPlan*> plans;
+    void *fb_table_g1 = nullptr, *fb_table_g2 = nullptr;     // fixed-base window tables of the generators (setup.cu)
 };
 
 struct b200zk_pk {
@@ -175,6 +177,11 @@ int fr_convert_dev(b200zk_ctx* ctx, Slot& sl, const void* d_in, void* d_out, siz
 int qap_dev(b200zk_ctx* ctx, Slot& sl, const void* a_ptr, const void* a_col, const void* a_val, const void* b_ptr,
             const void* b_col, const void* b_val, size_t nc, size_t n_inputs, const void* d_z, unsigned log_m, void* d_a,
             void* d_b, void* d_c);
+// setup.cu
+int fixed_base_mul_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_scalars, size_t n, void* d_out);
+int fr_powers_dev(b200zk_ctx* ctx, Slot& sl, const uint64_t base[4], const uint64_t scale[4], size_t n, void* d_out);
+int spmv_dev(b200zk_ctx* ctx, Slot& sl, const void* ptr, const void* idx, const void* val, const void* x, size_t n_rows, void* out);
+int fr_lincomb_dev(b200zk_ctx* ctx, Slot& sl, const void* a, const void* b, const void* c, const uint64_t s[16], size_t n, void* out);
 // prove.cu
 int assemble_dev(b200zk_ctx* ctx, Slot& sl, const b200zk_pk* pk, const void* msm_a, const void* msm_b2, const void* msm_l,
                  const void* msm_h, const void* msm_b1, const uint64_t r[4], const uint64_t s[4], int include_zero_terms,

@@ -170,6 +170,19 @@ int b200zk_groth16_assemble_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const void
                                 const void* d_msm_l, const void* d_msm_h, const void* d_msm_b1_or_null,
                                 const uint64_t r[4], const uint64_t s[4], int include_zero_terms, uint8_t proof_out[128]);
 
+/* ---- circuit-specific setup building blocks (Groth16::circuit_specific_setup in the reference's drivers,
+ *      groth16/examples/sha256.rs:133-137; h-query per ark-circom/src/circom/qap.rs:94-110) ------------------------ */
+/* out[i] = scalars[i] * G (generator of G1, or of G2 when g2 != 0); scalars Montgomery, out affine. */
+int b200zk_fixed_base_mul_dev(b200zk_ctx* ctx, int g2, const void* d_scalars, size_t n, void* d_out);
+/* out[i] = scale * base^i  (base, scale: 4 limbs Montgomery, host). */
+int b200zk_fr_powers_dev(b200zk_ctx* ctx, const uint64_t base[4], const uint64_t scale[4], size_t n, void* d_out);
+/* Generic CSR mat-vec over Fr: out[r] = sum val[k] x[idx[k]], k in [ptr[r], ptr[r+1]). */
+int b200zk_fr_spmv_dev(b200zk_ctx* ctx, const void* d_ptr, const void* d_idx, const void* d_val, const void* d_x,
+                       size_t n_rows, void* d_out);
+/* out[i] = (a[i] s0 + b[i] s1 + c[i] s2) s3   (s: 16 limbs = 4 Montgomery scalars, host). */
+int b200zk_fr_lincomb_dev(b200zk_ctx* ctx, const void* d_a, const void* d_b, const void* d_c, const uint64_t s[16], size_t n,
+                          void* d_out);
+
 /* ---- deterministic dummy inputs (groth16/examples/local_groth_bench.rs:21-52,
  *      groth16/src/proving_key.rs:112-155 generate dummy CRS points the same way: not a setup) ---- */
 int b200zk_g1_generate_dev(b200zk_ctx* ctx, uint64_t seed, size_t n, void* d_out);

@@ -197,3 +197,32 @@ def test_config4_sha256_circuit_shape_qap_h_and_prove(net, cref):
     got = circom.prove_from_matrices(pk, mats, z, mirror_reference_bg1=True)
     assert got == exp
     pk.free()
+
+
+def test_f3_gpu_setup_then_prove_sha256_and_verify_with_the_oracle_pairing(net):
+    """SURVEY f3 + config 4 closed end to end: circuit-specific setup ON THE GPU for the reference's sha256 circuit (known
+    trapdoor, like the reference's fixed-seed setup), GPU prove with the real witness, and the proof VERIFIES under the
+    oracle's pairing for the public input asserted in groth16/examples/sha256.rs:231-233 -- and fails for another input."""
+    import os
+    from oracle import bn254 as o, layout
+    from distributed_groth16_b200.groth16 import circom, setup
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sha256_circuit.npz"))
+    n_wires, n_pub, n_cons = (int(x) for x in d["dims"])
+    n_inputs = n_pub + 1
+    toxic = (0x1234567890ABCDEF1234567890ABCDEF % o.R, 11111111111111111111, 22222222222222222223, 33333333333333333337,
+             44444444444444444447)
+    coo = lambda k: (d[k + "_rows"], d[k + "_cols"], d[k + "_vals"])
+    pk, vk, mats = setup.circuit_specific_setup(net, n_wires, n_inputs, n_cons, coo("a"), coo("b"), coo("c"), toxic)
+    z = net.fr_convert(net.to_device(d["witness"]), to_mont=True)
+    for r, s in ((0, 0), (987654321, 123456789)):
+        proof = circom.prove_from_matrices(pk, mats, z, layout.fr_to_arr([r])[0], layout.fr_to_arr([s])[0])
+        A, B, C = o.proof_decompress(proof)
+        g1 = lambda a: layout.arr_to_g1(a)[0]
+        g2 = lambda a: layout.arr_to_g2(a)[0]
+        ic = layout.arr_to_g1(vk.gamma_abc_g1)
+        pub = int.from_bytes(d["witness"][1].tobytes(), "little")
+        assert pub == 72587776472194017031617589674261467945970986113287823188107011979
+        args = (g1(vk.alpha_g1), g2(vk.beta_g2), g2(vk.gamma_g2), g2(vk.delta_g2), ic)
+        assert o.groth16_verify(*args, [pub], A, B, C), (r, s)
+        assert not o.groth16_verify(*args, [pub + 1], A, B, C)
+    pk.free()
