@@ -187,6 +187,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("B200ZK_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"        # NCCL prints its banner on stdout; rank 0 must print ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     warm = max(args.warmup, 3)
     n = 1 << LOG_N

@@ -42,8 +42,12 @@ int b200zk_ctx_create(int device, b200zk_ctx** out) {
             return B200ZK_ERR_CUDA;
         }
         ctx->slots[i].owns_stream = true;
-        if (cudaStreamCreateWithFlags(&ctx->slots[i].copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ctx->slots[i].copy_done, cudaEventDisableTiming) != cudaSuccess) {
+        bool ok = cudaStreamCreateWithFlags(&ctx->slots[i].copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&ctx->slots[i].aux_stream, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&ctx->slots[i].copy_done, cudaEventDisableTiming) == cudaSuccess &&
+                  cudaEventCreateWithFlags(&ctx->slots[i].aux_done, cudaEventDisableTiming) == cudaSuccess;
+        for (int k = 0; ok && k < 4; ++k) ok = cudaEventCreateWithFlags(&ctx->slots[i].stage_ev[k], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) {
             delete ctx;
             return B200ZK_ERR_CUDA;
         }
@@ -63,8 +67,12 @@ void b200zk_ctx_destroy(b200zk_ctx* ctx) {
         Slot& s = ctx->slots[i];
         s.ws_msm.release(); s.ws_ntt.release(); s.io_a.release(); s.io_b.release(); s.small.release();
         if (s.owns_stream && s.stream) cudaStreamDestroy(s.stream);
+        s.ws_msm_aux.release();
         if (s.copy_stream) cudaStreamDestroy(s.copy_stream);
+        if (s.aux_stream) cudaStreamDestroy(s.aux_stream);
         if (s.copy_done) cudaEventDestroy(s.copy_done);
+        if (s.aux_done) cudaEventDestroy(s.aux_done);
+        for (int k = 0; k < 4; ++k) if (s.stage_ev[k]) cudaEventDestroy(s.stage_ev[k]);
     }
     for (auto& e : ctx->prof_pending) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
     delete ctx;
@@ -163,6 +171,31 @@ static int msm_host(b200zk_ctx* ctx, int stream, const uint64_t* bases, size_t n
     B2_CUDA_OK(ctx, sl.small.reserve(1024));
     char* d_bases = reinterpret_cast<char*>(sl.io_a.p);
     char* d_scalars = d_bases + n * PB;
+    static const bool split_env = !(getenv("B200ZK_MSM_SPLIT") && getenv("B200ZK_MSM_SPLIT")[0] == '0');
+    if (!G2 && split_env && n >= ((size_t)1 << 18)) {
+        // two halves, two compute streams: H2D order scalars-1, bases-1, scalars-2, bases-2 on the copy stream
+        const size_t n1 = n / 2, n2 = n - n1;
+        const char* hb = reinterpret_cast<const char*>(bases);
+        const char* hs = reinterpret_cast<const char*>(scalars);
+        cudaStream_t cs = sl.copy_stream;
+        B2_CUDA_OK(ctx, cudaMemcpyAsync(d_scalars, hs, n1 * 32, cudaMemcpyHostToDevice, cs));
+        B2_CUDA_OK(ctx, cudaEventRecord(sl.stage_ev[0], cs));
+        B2_CUDA_OK(ctx, cudaMemcpyAsync(d_bases, hb, n1 * PB, cudaMemcpyHostToDevice, cs));
+        B2_CUDA_OK(ctx, cudaEventRecord(sl.stage_ev[1], cs));
+        B2_CUDA_OK(ctx, cudaMemcpyAsync(d_scalars + n1 * 32, hs + n1 * 32, n2 * 32, cudaMemcpyHostToDevice, cs));
+        B2_CUDA_OK(ctx, cudaEventRecord(sl.stage_ev[2], cs));
+        B2_CUDA_OK(ctx, cudaMemcpyAsync(d_bases + n1 * PB, hb + n1 * PB, n2 * PB, cudaMemcpyHostToDevice, cs));
+        B2_CUDA_OK(ctx, cudaEventRecord(sl.stage_ev[3], cs));
+        char* sm2 = reinterpret_cast<char*>(sl.small.p);
+        B2_TRY(msm_g1_two_halves_dev(ctx, sl, d_bases, d_scalars, n1, n2, sl.stage_ev, sm2));
+        B2_TRY(g1_sum_dev(ctx, sl, sm2, 2, sm2 + 256));
+        uint64_t host2[9];
+        B2_CUDA_OK(ctx, cudaMemcpyAsync(host2, sm2 + 256, PB + 8, cudaMemcpyDeviceToHost, sl.stream));
+        B2_CUDA_OK(ctx, cudaStreamSynchronize(sl.stream));
+        memcpy(out_affine, host2, PB);
+        *out_is_inf = (int)host2[PB / 8];
+        return B200ZK_OK;
+    }
     if (n) {
         // scalars first on the compute stream; the bases travel on the copy stream while digits/sort run
         B2_CUDA_OK(ctx, cudaMemcpyAsync(d_scalars, scalars, n * 32, cudaMemcpyHostToDevice, sl.stream));

@@ -49,6 +49,9 @@ struct Slot {                 // one per MultiplexedStreamID
     DevBuf small;             // results
     cudaStream_t copy_stream = nullptr;   // second stream for overlapped H2D staging (host-buffer entry points)
     cudaEvent_t copy_done = nullptr;
+    cudaStream_t aux_stream = nullptr;    // second compute stream + workspace: host-staged MSMs run as two halves
+    DevBuf ws_msm_aux;
+    cudaEvent_t aux_done = nullptr, stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 }  // namespace b200zk
@@ -166,6 +169,8 @@ int msm_g1_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_sca
                cudaEvent_t bases_ready = nullptr);
 int msm_g2_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n, void* d_out_xyzz,
                cudaEvent_t bases_ready = nullptr);
+int msm_g1_two_halves_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n1, size_t n2,
+                          cudaEvent_t ev[4], void* d_out2);
 int g1_sum_dev(b200zk_ctx* ctx, Slot& sl, const void* d_xyzz, size_t count, void* d_out_affine);
 int g2_sum_dev(b200zk_ctx* ctx, Slot& sl, const void* d_xyzz, size_t count, void* d_out_affine);
 int xyzz_sum_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_in, size_t count, size_t stride, void* d_out);

@@ -451,9 +451,9 @@ static int exclusive_scan(b200zk_ctx* ctx, cudaStream_t st, const uint32_t* in, 
 }
 
 template <class F>
-static int msm_dev_impl(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n, void* d_out,
-                        const char* acc_name, cudaEvent_t bases_ready) {
-    cudaStream_t st = sl.stream;
+static int msm_dev_impl(b200zk_ctx* ctx, cudaStream_t st, DevBuf& ws_buf, const void* d_bases, const void* d_scalars, size_t n,
+                        void* d_out, const char* acc_name, cudaEvent_t bases_ready, cudaEvent_t scalars_ready = nullptr) {
+    if (scalars_ready) B2_CUDA_OK(ctx, cudaStreamWaitEvent(st, scalars_ready, 0));
     xyzz_t<F>* out = reinterpret_cast<xyzz_t<F>*>(d_out);
     if (n == 0) {
         LaunchScope ls(ctx, st, "msm_small");
@@ -494,8 +494,8 @@ static int msm_dev_impl(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const vo
     size_t o_partials = o_buckets + al((size_t)nb * sizeof(xyzz_t<F>));
     size_t o_wsum = o_partials + al((size_t)W * nseg * sizeof(xyzz_t<F>));
     size_t ws_bytes = o_wsum + al((size_t)W * sizeof(xyzz_t<F>));
-    B2_CUDA_OK(ctx, sl.ws_msm.reserve(ws_bytes));
-    char* ws = reinterpret_cast<char*>(sl.ws_msm.p);
+    B2_CUDA_OK(ctx, ws_buf.reserve(ws_bytes));
+    char* ws = reinterpret_cast<char*>(ws_buf.p);
     uint32_t* keys = reinterpret_cast<uint32_t*>(ws + o_keys);
     uint32_t* ranks = reinterpret_cast<uint32_t*>(ws + o_ranks);
     uint32_t* entries = reinterpret_cast<uint32_t*>(ws + o_entries);
@@ -613,11 +613,27 @@ static int msm_dev_impl(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const vo
 
 int msm_g1_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n, void* d_out,
                cudaEvent_t bases_ready) {
-    return msm_dev_impl<Fq>(ctx, sl, d_bases, d_scalars, n, d_out, "msm_accumulate_g1", bases_ready);
+    return msm_dev_impl<Fq>(ctx, sl.stream, sl.ws_msm, d_bases, d_scalars, n, d_out, "msm_accumulate_g1", bases_ready);
 }
 int msm_g2_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n, void* d_out,
                cudaEvent_t bases_ready) {
-    return msm_dev_impl<Fq2>(ctx, sl, d_bases, d_scalars, n, d_out, "msm_accumulate_g2", bases_ready);
+    return msm_dev_impl<Fq2>(ctx, sl.stream, sl.ws_msm, d_bases, d_scalars, n, d_out, "msm_accumulate_g2", bases_ready);
+}
+
+// Host-staged G1 MSM in two halves on two streams: the H2D copy of the second half and the latency-bound tail of the
+// first half overlap the bucket accumulation of the other half (the PCIe transfer is ~1/3 of the end-to-end time).
+// d_bases / d_scalars are the device staging buffers the caller is filling on `copy_stream`; ev[0..3] are recorded by the
+// caller after scalars-1, bases-1, scalars-2, bases-2 have been queued.  d_out2: two XYZZ partials.
+int msm_g1_two_halves_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n1, size_t n2,
+                          cudaEvent_t ev[4], void* d_out2) {
+    const char* b = reinterpret_cast<const char*>(d_bases);
+    const char* s = reinterpret_cast<const char*>(d_scalars);
+    char* out = reinterpret_cast<char*>(d_out2);
+    B2_TRY(msm_dev_impl<Fq>(ctx, sl.stream, sl.ws_msm, b, s, n1, out, "msm_accumulate_g1", ev[1], ev[0]));
+    B2_TRY(msm_dev_impl<Fq>(ctx, sl.aux_stream, sl.ws_msm_aux, b + n1 * 64, s + n1 * 32, n2, out + 128, "msm_accumulate_g1", ev[3], ev[2]));
+    B2_CUDA_OK(ctx, cudaEventRecord(sl.aux_done, sl.aux_stream));
+    B2_CUDA_OK(ctx, cudaStreamWaitEvent(sl.stream, sl.aux_done, 0));
+    return B200ZK_OK;
 }
 
 // out = sum of `count` XYZZ points at pts[i * stride] (no normalisation): combines gathered per-rank partials
