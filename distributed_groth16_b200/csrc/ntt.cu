@@ -127,6 +127,9 @@ struct PassParams {
     Fr* peer_out[8];
     uint32_t p2p, log_rl, log_cols_total;
     uint64_t col0;
+    // last pass only: the G columns of a block are G consecutive BATCH elements (same sub-problem j = blockIdx.x) instead
+    // of G consecutive j of one batch element, so that the remote stores of the fused exchange are runs of G x 32 B
+    uint32_t batch_tile;
 };
 
 __global__ void __launch_bounds__(512) k_ntt_pass(PassParams p) {
@@ -137,9 +140,8 @@ __global__ void __launch_bounds__(512) k_ntt_pass(PassParams p) {
     uint4* s_hi = smem + RG;
     uint4* s_tw = smem + 2 * RG;        // [R/2][2]
     const uint32_t tid = threadIdx.x, nt = blockDim.x;
-    const Fr* in = p.in + (size_t)blockIdx.y * p.batch_stride;
-    Fr* out = p.out + (size_t)blockIdx.y * p.batch_stride;
-    const uint64_t q0 = (uint64_t)blockIdx.x << p.logG;
+    const uint64_t q0 = p.batch_tile ? (uint64_t)blockIdx.x : ((uint64_t)blockIdx.x << p.logG);
+    const uint32_t b0 = p.batch_tile ? (blockIdx.y << p.logG) : blockIdx.y;
     const uint64_t Mmask = (1ull << p.logM) - 1;
 
     for (uint32_t i = tid; i < R / 2; i += nt) {
@@ -149,8 +151,9 @@ __global__ void __launch_bounds__(512) k_ntt_pass(PassParams p) {
     }
     for (uint32_t idx = tid; idx < RG; idx += nt) {
         uint32_t c = idx & (G - 1), ns = idx >> p.logG;
-        uint64_t q = q0 + c, j = q >> p.logM, n2 = q & Mmask;
+        uint64_t q = p.batch_tile ? q0 : q0 + c, j = q >> p.logM, n2 = q & Mmask;
         uint64_t addr = (j << (p.logR + p.logM)) + ((uint64_t)ns << p.logM) + n2;
+        const Fr* in = p.in + (size_t)(p.batch_tile ? b0 + c : b0) * p.batch_stride;
         Fr v = ld_fr(in + addr);
         if (p.apply_pre) v = Fr::mul(v, powtab_get(p.pre, addr));
         uint32_t slot = p.logR ? (__brev(ns) >> (32 - p.logR)) : 0;
@@ -189,7 +192,9 @@ __global__ void __launch_bounds__(512) k_ntt_pass(PassParams p) {
 
     for (uint32_t idx = tid; idx < RG; idx += nt) {
         uint32_t c = idx & (G - 1), ks = idx >> p.logG;
-        uint64_t q = q0 + c, j = q >> p.logM, n2 = q & Mmask;
+        uint64_t q = p.batch_tile ? q0 : q0 + c, j = q >> p.logM, n2 = q & Mmask;
+        const uint32_t bidx = p.batch_tile ? b0 + c : b0;
+        Fr* out = p.out + (size_t)bidx * p.batch_stride;
         uint32_t e = c * R + ks;
         uint4 a = s_lo[e], bq = s_hi[e];
         Fr v;
@@ -200,12 +205,12 @@ __global__ void __launch_bounds__(512) k_ntt_pass(PassParams p) {
         }
         uint64_t oaddr = ((j + ((uint64_t)ks << p.logL)) << p.logM) + n2;
         if (p.apply_post) {
-            uint64_t ex = (blockIdx.y + p.post_b0) * (p.post_alpha * oaddr + p.post_beta) + p.post_gamma * oaddr;
+            uint64_t ex = (bidx + p.post_b0) * (p.post_alpha * oaddr + p.post_beta) + p.post_gamma * oaddr;
             if (ex) v = Fr::mul(v, powtab_get(p.post, ex));
         }
         if (p.apply_post_const) v = Fr::mul(v, ld_fr(p.post_const));
         if (p.p2p) {
-            Fr* dst = p.peer_out[oaddr >> p.log_rl] + ((oaddr & ((1ull << p.log_rl) - 1)) << p.log_cols_total) + p.col0 + blockIdx.y;
+            Fr* dst = p.peer_out[oaddr >> p.log_rl] + ((oaddr & ((1ull << p.log_rl) - 1)) << p.log_cols_total) + p.col0 + bidx;
             st_fr(dst, v);
         } else {
             st_fr(out + oaddr, v);
@@ -375,6 +380,14 @@ static int ntt_run(b200zk_ctx* ctx, Slot& sl, NttPlan* pl, const Fr* d_in, Fr* d
         uint32_t threads = RG / tdiv < 32 ? 32 : RG / tdiv;
         size_t smem = (size_t)(2 * RG + (1u << p.logR)) * sizeof(uint4);
         dim3 grid((unsigned)(((size_t)1 << log_cols) >> p.logG), batch);
+        if (last && p2p && p.logM == 0 && batch >= (1u << LOG_G) && batch % (1u << LOG_G) == 0) {
+            p.batch_tile = 1;
+            p.logG = LOG_G;
+            RG = 1u << (p.logR + p.logG);
+            threads = RG / tdiv < 32 ? 32 : RG / tdiv;
+            smem = (size_t)(2 * RG + (1u << p.logR)) * sizeof(uint4);
+            grid = dim3((unsigned)((size_t)1 << log_cols), batch >> LOG_G);
+        }
         {
             LaunchScope ls(ctx, st, "ntt_pass");
             k_ntt_pass<<<grid, threads, smem, st>>>(p);
