@@ -62,3 +62,77 @@ def d_msm(bases, scalars, pp=None, net: Net | None = None, sid: MultiplexedStrea
     else:
         limbs, inf = net.sum_points_dev(part, 1, g2=g2, sid=int(sid))
     return GroupElement(limbs, inf, g2)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's MPC protocol on top of the GPU kernels: packed secret sharing "in the exponent".
+# ---------------------------------------------------------------------------------------------------------------------
+_FR = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+_GEN = 5
+
+
+def _fr_limbs_mont(values):
+    """canonical ints -> Montgomery limbs; integer arithmetic on the O(n^2), n <= 16, domain constants only."""
+    rows = []
+    for v in values:
+        x = (v % _FR) * (1 << 256) % _FR
+        rows.append([(x >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)])
+    return np.array(rows, dtype=np.uint64)
+
+
+def _group_dft(net, points, size: int, inverse: bool, coset: bool, g2: bool):
+    """FFT / iFFT of group elements over a radix-2 domain of `size` (offset = generator when `coset`): what
+    `domain.fft_in_place(&mut Vec<G>)` does in unpackexp / packexp (dmsm/mod.rs:14,38,45,55,58).  Row i of the DFT matrix
+    is a `size`-term MSM, executed by the Pippenger kernels."""
+    w = 16 if g2 else 8
+    pts = np.zeros((size, w), dtype=np.uint64)
+    p = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, w)
+    pts[: min(size, p.shape[0])] = p[: min(size, p.shape[0])]
+    omega = pow(_GEN, (_FR - 1) // size, _FR)
+    if inverse:
+        omega = pow(omega, -1, _FR)
+    out = np.zeros((size, w), dtype=np.uint64)
+    ninv = pow(size, -1, _FR)
+    for i in range(size):
+        if not inverse:
+            sc = [pow(omega, i * j, _FR) * (pow(_GEN, j, _FR) if coset else 1) for j in range(size)]
+        else:
+            scale = ninv * (pow(_GEN, -i, _FR) if coset else 1)
+            sc = [pow(omega, i * j, _FR) * scale for j in range(size)]
+        limbs, inf = net.msm(pts, _fr_limbs_mont(sc), g2=g2)
+        if not inf:
+            out[i] = limbs
+    return out
+
+
+def packexp_from_public(secrets, pp, net: Net, g2: bool = False) -> np.ndarray:
+    """dmsm/mod.rs:50-68: pack l group elements into n shares (iFFT over `secret`, FFT over `share`)."""
+    c = _group_dft(net, secrets, pp.secret_size, inverse=True, coset=True, g2=g2)
+    return _group_dft(net, c, pp.share_size, inverse=False, coset=False, g2=g2)
+
+
+def unpackexp(shares, degree2: bool, pp, net: Net, g2: bool = False) -> np.ndarray:
+    """dmsm/mod.rs:7-48: interpolate the n shares, evaluate on the secret (or secret2) coset, keep the secrets."""
+    c = _group_dft(net, shares, pp.share_size, inverse=True, coset=False, g2=g2)
+    if degree2:
+        e = _group_dft(net, c, pp.secret2_size, inverse=False, coset=True, g2=g2)
+        return e[: 2 * pp.l: 2]
+    e = _group_dft(net, c, pp.secret_size, inverse=False, coset=True, g2=g2)
+    return e[: pp.l]
+
+
+def d_msm_mpc(bases_shares, scalar_shares, pp, net: Net, g2: bool = False) -> GroupElement:
+    """The reference protocol itself, all n parties simulated on this GPU (what LocalTestNet does in-process,
+    mpc-net/src/multi.rs:289-316): every party runs `G::msm` on its packed shares (dmsm/mod.rs:82); the king unpacks the
+    degree-2 sharing in the exponent and sums the l secrets (dmsm/mod.rs:91-95).
+    bases_shares[p], scalar_shares[p]: party p's share vectors."""
+    w = 16 if g2 else 8
+    c_shares = np.zeros((pp.n, w), dtype=np.uint64)
+    for p in range(pp.n):
+        limbs, inf = net.msm(bases_shares[p], scalar_shares[p], g2=g2)
+        if not inf:
+            c_shares[p] = limbs
+    secrets = unpackexp(c_shares, True, pp, net, g2=g2)
+    ones = _fr_limbs_mont([1] * secrets.shape[0])
+    limbs, inf = net.msm(secrets, ones, g2=g2)
+    return GroupElement(limbs, inf, g2)
