@@ -44,6 +44,9 @@ SIGNATURES = {
                                      ctypes.POINTER(ctypes.c_int)]),
     "b200zk_msm_g1_dev": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "b200zk_msm_g2_dev": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_size_t, c_vp]),
+    "b200zk_msm_table_windows": (ctypes.c_uint, [ctypes.c_uint]),
+    "b200zk_msm_table_build_dev": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_size_t, ctypes.c_uint, c_vp]),
+    "b200zk_msm_table_dev": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp, ctypes.c_size_t, ctypes.c_uint, c_vp]),
     "b200zk_g1_sum_dev": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, ctypes.c_size_t, c_vp, ctypes.POINTER(ctypes.c_int)]),
     "b200zk_g2_sum_dev": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, ctypes.c_size_t, c_vp, ctypes.POINTER(ctypes.c_int)]),
     "b200zk_ntt_fr": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, ctypes.c_uint, ctypes.c_int, ctypes.c_int, ctypes.c_int,
@@ -74,6 +77,8 @@ SIGNATURES = {
                                             ctypes.c_size_t, c_vp, ctypes.POINTER(c_vp)]),
     "b200zk_groth16_prove_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp]),
     "b200zk_pk_free": (None, [c_vp, c_vp]),
+    "b200zk_pk_precompute": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint]),
+    "b200zk_pk_table_bytes": (ctypes.c_size_t, [c_vp]),
     "b200zk_groth16_prove": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp]),
     "b200zk_xyzz_sum_dev": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_size_t, ctypes.c_size_t, c_vp]),
     "b200zk_groth16_assemble_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp]),

@@ -193,6 +193,32 @@ class Net:
         self.check(fn(self._h, int(sid), c_vp(bases.data_ptr()), c_vp(scalars.data_ptr()), n, c_vp(out_xyzz.data_ptr())))
         return out_xyzz
 
+    def msm_table_windows(self, c: int) -> int:
+        return int(self._lib.b200zk_msm_table_windows(int(c)))
+
+    def msm_table_build(self, bases, c: int, g2: bool = False, sid: int = 0):
+        """Fixed-base window table of `bases` (CUDA int64, n x 8 / n x 16): (windows * n) points, table[w*n+i] =
+        2^{c w} * bases[i].  For bases that stay resident across calls (a proving key's query vectors)."""
+        import torch
+        n = int(bases.shape[0])
+        w = self.msm_table_windows(c)
+        table = torch.empty((w * n, 16 if g2 else 8), dtype=torch.int64, device=bases.device)
+        self.check(self._lib.b200zk_msm_table_build_dev(self._h, int(sid), 1 if g2 else 0, c_vp(bases.data_ptr()), n, int(c),
+                                                        c_vp(table.data_ptr())))
+        return table
+
+    def msm_table_dev(self, table, scalars, c: int, out_xyzz=None, g2: bool = False, sid: int = 0):
+        """Same sum as msm_dev(bases, scalars) from the table msm_table_build(bases, c) made."""
+        import torch
+        n = int(scalars.shape[0])
+        if int(table.shape[0]) != n * self.msm_table_windows(c):
+            raise MpcNetError("Generic", str(min(n, int(table.shape[0]) // max(self.msm_table_windows(c), 1))))
+        if out_xyzz is None:
+            out_xyzz = torch.empty(32 if g2 else 16, dtype=torch.int64, device=table.device)
+        self.check(self._lib.b200zk_msm_table_dev(self._h, int(sid), 1 if g2 else 0, c_vp(table.data_ptr()),
+                                                  c_vp(scalars.data_ptr()), n, int(c), c_vp(out_xyzz.data_ptr())))
+        return out_xyzz
+
     def sum_points_dev(self, xyzz, count: int, g2: bool = False, sid: int = 0):
         w = 16 if g2 else 8
         out = np.zeros(w, dtype=np.uint64)

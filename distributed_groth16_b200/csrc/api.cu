@@ -255,6 +255,21 @@ int b200zk_msm_g2_dev(b200zk_ctx* ctx, int stream, const void* d_bases, const vo
     return msm_g2_dev(ctx, sl, d_bases, d_scalars, n, d_out);
 }
 
+unsigned b200zk_msm_table_windows(unsigned c) { return c ? msm_table_windows(c) : 0; }
+int b200zk_msm_table_build_dev(b200zk_ctx* ctx, int stream, int g2, const void* d_bases, size_t n, unsigned c, void* d_table) {
+    if (!ctx || !valid_slot(stream) || (n && (!d_bases || !d_table))) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[stream];
+    std::lock_guard<std::mutex> g(sl.mu);
+    return msm_table_build_dev(ctx, sl, g2, d_bases, n, c, d_table);
+}
+int b200zk_msm_table_dev(b200zk_ctx* ctx, int stream, int g2, const void* d_table, const void* d_scalars, size_t n, unsigned c,
+                         void* d_out) {
+    if (!ctx || !valid_slot(stream) || !d_out) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[stream];
+    std::lock_guard<std::mutex> g(sl.mu);
+    return msm_table_dev(ctx, sl, g2, d_table, d_scalars, n, c, d_out);
+}
+
 int b200zk_g1_sum_dev(b200zk_ctx* ctx, int stream, const void* d, size_t count, uint64_t out[8], int* inf) {
     return sum_host<0>(ctx, stream, d, count, out, inf);
 }
@@ -430,6 +445,12 @@ static int pk_build(b200zk_ctx* ctx, const void* a_query, const void* b_g1_query
     if (!rc) rc = upload(ctx, &pk->h_query, h_query, m * 64, kind);
     if (!rc) rc = upload(ctx, &pk->vk, vk_points, 56 * 8);
     if (rc) { b200zk_pk_free(ctx, pk); return rc; }
+    const char* env = getenv("B200ZK_PK_TABLES");
+    if (!(env && env[0] == '0')) {
+        std::lock_guard<std::mutex> g(ctx->slots[0].mu);
+        rc = pk_precompute_dev(ctx, pk, 0);
+        if (rc) { b200zk_pk_free(ctx, pk); return rc; }
+    }
     *out = pk;
     return B200ZK_OK;
 }
@@ -452,8 +473,18 @@ void b200zk_pk_free(b200zk_ctx* ctx, b200zk_pk* pk) {
     if (ctx) cudaSetDevice(ctx->device);
     void* ptrs[6] = {pk->a_query, pk->b_g1_query, pk->b_g2_query, pk->l_query, pk->h_query, pk->vk};
     for (void* p : ptrs) if (p) cudaFree(p);
+    pk_free_tables(pk);
     delete pk;
 }
+
+int b200zk_pk_precompute(b200zk_ctx* ctx, b200zk_pk* pk, unsigned c) {
+    if (!ctx || !pk) return B200ZK_ERR_ARG;
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    std::lock_guard<std::mutex> g(ctx->slots[0].mu);
+    if (c == 0xFFFFFFFFu) { pk_free_tables(pk); return B200ZK_OK; }
+    return pk_precompute_dev(ctx, pk, c);
+}
+size_t b200zk_pk_table_bytes(const b200zk_pk* pk) { return pk ? pk->tab_bytes : 0; }
 
 int b200zk_groth16_prove(b200zk_ctx* ctx, const b200zk_pk* pk, const uint64_t* z, const uint64_t* a, const uint64_t* b,
                          const uint64_t* c, const uint64_t r[4], const uint64_t s[4], int mirror_bg1, uint8_t proof_out[128]) {

@@ -80,6 +80,11 @@ struct b200zk_pk {
     size_t n_vars = 0, n_inputs = 0, m = 0;
     void *a_query = nullptr, *b_g1_query = nullptr, *b_g2_query = nullptr, *l_query = nullptr, *h_query = nullptr;
     void* vk = nullptr;       // device copy of the 56 vk limbs
+    // fixed-base window tables (msm.cu section 7) over a_query[1..], b_g1_query[1..], b_g2_query[1..], l_query, h_query;
+    // tab_c[k] == 0: no table, the generic MSM runs on the query itself
+    void* tab[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned tab_c[5] = {0, 0, 0, 0, 0};
+    size_t tab_bytes = 0;
 };
 
 namespace b200zk {
@@ -171,6 +176,10 @@ int msm_g2_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_sca
                cudaEvent_t bases_ready = nullptr);
 int msm_g1_two_halves_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n1, size_t n2,
                           cudaEvent_t ev[4], void* d_out2);
+unsigned msm_table_windows(unsigned c);
+int msm_table_build_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_bases, size_t n, unsigned c, void* d_table);
+int msm_table_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_table, const void* d_scalars, size_t n, unsigned c,
+                  void* d_out_xyzz);
 int g1_sum_dev(b200zk_ctx* ctx, Slot& sl, const void* d_xyzz, size_t count, void* d_out_affine);
 int g2_sum_dev(b200zk_ctx* ctx, Slot& sl, const void* d_xyzz, size_t count, void* d_out_affine);
 int xyzz_sum_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_in, size_t count, size_t stride, void* d_out);
@@ -191,6 +200,8 @@ int fr_lincomb_dev(b200zk_ctx* ctx, Slot& sl, const void* a, const void* b, cons
 int assemble_dev(b200zk_ctx* ctx, Slot& sl, const b200zk_pk* pk, const void* msm_a, const void* msm_b2, const void* msm_l,
                  const void* msm_h, const void* msm_b1, const uint64_t r[4], const uint64_t s[4], int include_zero_terms,
                  uint8_t proof_out[128]);
+int pk_precompute_dev(b200zk_ctx* ctx, b200zk_pk* pk, unsigned c);
+void pk_free_tables(b200zk_pk* pk);
 int prove_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, const Fr* d_a, const Fr* d_b, const Fr* d_c,
               const uint64_t r[4], const uint64_t s[4], int mirror_bg1, uint8_t proof_out[128]);
 

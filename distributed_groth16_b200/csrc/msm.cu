@@ -44,8 +44,10 @@ __device__ __forceinline__ void st16(T* p, const T& v) {
 // ---------------------------------------------------------------------------------------------
 // 1. digits + histogram
 // ---------------------------------------------------------------------------------------------
-__global__ void k_msm_digits(const Fr* scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t* keys, uint32_t* ranks,
-                             uint32_t* counts) {
+// fold != 0 (fixed-base tables, section 7): every window shares ONE bucket set, the window is carried by the
+// entry index (w * n + i selects 2^{cw} P_i in the table) instead of by the bucket index
+__global__ void k_msm_digits(const Fr* scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t fold, uint32_t* keys,
+                             uint32_t* ranks, uint32_t* counts) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Fr s = Fr::from_mont(ld16(scalars + i));
@@ -65,7 +67,7 @@ __global__ void k_msm_digits(const Fr* scalars, uint32_t n, uint32_t c, uint32_t
         uint32_t neg = 0;
         if (d > B) { d = (1u << c) - d; neg = 1; carry = 1; }
         if (d != 0) {
-            uint32_t g = w * B + (d - 1);
+            uint32_t g = (fold ? 0u : w * B) + (d - 1);
             rank = atomicAdd(counts + g, 1u);
             key = g | (neg << 31);
         }
@@ -181,12 +183,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t* out, const 
 // 3. scatter
 // ---------------------------------------------------------------------------------------------
 __global__ void k_msm_scatter(const uint32_t* keys, const uint32_t* ranks, const uint32_t* offsets, uint32_t n,
-                              size_t total, uint32_t* entries) {
+                              size_t total, uint32_t fold, uint32_t* entries) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
     uint32_t key = keys[t];
     if (key == KEY_NONE) return;
-    uint32_t i = (uint32_t)(t % n);
+    uint32_t i = fold ? (uint32_t)t : (uint32_t)(t % n);
     uint32_t g = key & 0x7FFFFFFFu;
     entries[offsets[g] + ranks[t]] = i | (key & 0x80000000u);
 }
@@ -201,6 +203,9 @@ __global__ void k_msm_scatter(const uint32_t* keys, const uint32_t* ranks, const
 static const uint32_t TASK_LEN = 128;
 #ifndef B2_ACC_MINBLOCKS
 #define B2_ACC_MINBLOCKS 4
+#endif
+#ifndef B2_ACC_MINBLOCKS_G2
+#define B2_ACC_MINBLOCKS_G2 2
 #endif
 
 __global__ void k_msm_task_counts(const uint32_t* offsets, uint32_t nbuckets, uint32_t* ntasks) {
@@ -258,7 +263,7 @@ __global__ void k_msm_task_order(const uint32_t* offsets, const uint32_t* task_o
 
 // G2 (Fq2 coordinates) needs ~2x the registers of G1: capping it at 128 spilled 1.1 KB/thread to local memory
 template <class F>
-__global__ void __launch_bounds__(128, sizeof(F) > 32 ? 2 : B2_ACC_MINBLOCKS) k_msm_accumulate(const affine_t<F>* bases, const uint32_t* entries, const uint32_t* offsets,
+__global__ void __launch_bounds__(128, sizeof(F) > 32 ? B2_ACC_MINBLOCKS_G2 : B2_ACC_MINBLOCKS) k_msm_accumulate(const affine_t<F>* bases, const uint32_t* entries, const uint32_t* offsets,
                                  const uint32_t* task_off, const uint32_t* task_bucket, const uint32_t* order,
                                  uint32_t nbuckets, xyzz_t<F>* buckets, xyzz_t<F>* task_sums) {
     uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -452,7 +457,8 @@ static int exclusive_scan(b200zk_ctx* ctx, cudaStream_t st, const uint32_t* in, 
 
 template <class F>
 static int msm_dev_impl(b200zk_ctx* ctx, cudaStream_t st, DevBuf& ws_buf, const void* d_bases, const void* d_scalars, size_t n,
-                        void* d_out, const char* acc_name, cudaEvent_t bases_ready, cudaEvent_t scalars_ready = nullptr) {
+                        void* d_out, const char* acc_name, cudaEvent_t bases_ready, cudaEvent_t scalars_ready = nullptr,
+                        unsigned tab_c = 0) {
     if (scalars_ready) B2_CUDA_OK(ctx, cudaStreamWaitEvent(st, scalars_ready, 0));
     xyzz_t<F>* out = reinterpret_cast<xyzz_t<F>*>(d_out);
     if (n == 0) {
@@ -461,16 +467,22 @@ static int msm_dev_impl(b200zk_ctx* ctx, cudaStream_t st, DevBuf& ws_buf, const 
         return check_launch(ctx, "k_set_identity");
     }
     if (n >= (1ull << 31)) return set_error(ctx, B200ZK_ERR_ARG, "MSM length must be < 2^31");
-    const unsigned c = choose_window(n);
+    // tab_c != 0: d_bases is a fixed-base table of msm_table_windows(tab_c) x n points (section 7); all digit windows
+    // then share one bucket set and the Horner chain disappears
+    const bool fold = tab_c != 0;
+    const unsigned c = fold ? tab_c : choose_window(n);
     static const bool glv_env = !(getenv("B200ZK_MSM_GLV") && getenv("B200ZK_MSM_GLV")[0] == '0');
-    const bool glv = glv_env && sizeof(F) == 32;             // G1 only (glv.cuh)
+    const bool glv = !fold && glv_env && sizeof(F) == 32;    // G1 only (glv.cuh)
     const unsigned Wh = (128 + c - 1) / c;                   // |k1|, |k2| < 2^127: Wh * c >= 128 leaves the carry room
-    const unsigned W = glv ? 2 * Wh : (255 + c - 1) / c;
-    if ((uint64_t)W * n >= (1ull << 32)) return set_error(ctx, B200ZK_ERR_ARG, "MSM too large for 32-bit bucket offsets (W * n >= 2^32)");
+    const unsigned W = glv ? 2 * Wh : (255 + c - 1) / c;     // digit windows
+    const unsigned WB = fold ? 1 : W;                        // bucket sets
+    if ((uint64_t)W * n >= (fold ? (1ull << 31) : (1ull << 32)))
+        return set_error(ctx, B200ZK_ERR_ARG, "MSM too large for 32-bit bucket offsets / entry indices (W * n)");
     const uint32_t B = 1u << (c - 1);
-    const uint32_t nb = W * B;
+    const uint32_t nb = WB * B;
     uint32_t seg_len = B < 16 ? B : 16;
     const uint32_t nseg = B / seg_len;
+    const uint32_t wsplit = (fold && nseg >= 16 * 256) ? 16 : 1;
     const size_t total = (size_t)W * n;
 
     // workspace carve-up (256-byte aligned)
@@ -492,8 +504,8 @@ static int msm_dev_impl(b200zk_ctx* ctx, cudaStream_t st, DevBuf& ws_buf, const 
     size_t o_tasksums = o_order + al(max_tasks * 4);
     size_t o_buckets = o_tasksums + al(max_tasks * sizeof(xyzz_t<F>));
     size_t o_partials = o_buckets + al((size_t)nb * sizeof(xyzz_t<F>));
-    size_t o_wsum = o_partials + al((size_t)W * nseg * sizeof(xyzz_t<F>));
-    size_t ws_bytes = o_wsum + al((size_t)W * sizeof(xyzz_t<F>));
+    size_t o_wsum = o_partials + al((size_t)WB * nseg * sizeof(xyzz_t<F>));
+    size_t ws_bytes = o_wsum + al((size_t)WB * wsplit * sizeof(xyzz_t<F>));
     B2_CUDA_OK(ctx, ws_buf.reserve(ws_bytes));
     char* ws = reinterpret_cast<char*>(ws_buf.p);
     uint32_t* keys = reinterpret_cast<uint32_t*>(ws + o_keys);
@@ -520,7 +532,7 @@ static int msm_dev_impl(b200zk_ctx* ctx, cudaStream_t st, DevBuf& ws_buf, const 
         if (glv) k_msm_digits_glv<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const Fr*>(d_scalars), (uint32_t)n, c,
                                                                               Wh, keys, ranks, counts);
         else k_msm_digits<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const Fr*>(d_scalars), (uint32_t)n, c, W,
-                                                                         keys, ranks, counts);
+                                                                         fold ? 1u : 0u, keys, ranks, counts);
     }
     B2_TRY(check_launch(ctx, "k_msm_digits"));
     B2_TRY(exclusive_scan(ctx, st, counts, offsets, sums, nb + 1));
@@ -553,7 +565,7 @@ static int msm_dev_impl(b200zk_ctx* ctx, cudaStream_t st, DevBuf& ws_buf, const 
     B2_TRY(check_launch(ctx, "k_msm_task_order"));
     {
         LaunchScope ls(ctx, st, "msm_scatter");
-        k_msm_scatter<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(keys, ranks, offsets, (uint32_t)n, total, entries);
+        k_msm_scatter<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(keys, ranks, offsets, (uint32_t)n, total, fold ? 1u : 0u, entries);
     }
     B2_TRY(check_launch(ctx, "k_msm_scatter"));
     // the digit / sort phases above only read the scalars: a caller staging host buffers lets the H2D copy of
@@ -594,19 +606,21 @@ static int msm_dev_impl(b200zk_ctx* ctx, cudaStream_t st, DevBuf& ws_buf, const 
     B2_TRY(check_launch(ctx, "k_msm_merge_tasks"));
     {
         LaunchScope ls(ctx, st, "msm_reduce");
-        k_msm_reduce_segments<F><<<(W * nseg + 127) / 128, 128, 0, st>>>(buckets, W, B, seg_len, partials);
+        k_msm_reduce_segments<F><<<(WB * nseg + 127) / 128, 128, 0, st>>>(buckets, WB, B, seg_len, partials);
     }
     B2_TRY(check_launch(ctx, "k_msm_reduce_segments"));
     {
         LaunchScope ls(ctx, st, "msm_window_sum");
         constexpr int T = sizeof(F) > 32 ? 128 : 256;
-        k_msm_window_sum<F, T><<<W, T, 0, st>>>(partials, nseg, wsum);
+        // fold: the single bucket set's partials are summed by FOLD_SPLIT blocks, then added up by the combine
+        // kernel with zero doublings per step
+        k_msm_window_sum<F, T><<<WB * wsplit, T, 0, st>>>(partials, nseg / wsplit, wsum);
     }
     B2_TRY(check_launch(ctx, "k_msm_window_sum"));
     {
         LaunchScope ls(ctx, st, "msm_combine");
         if (glv) k_msm_combine_glv<<<1, 32, 0, st>>>(reinterpret_cast<const xyzz_t<Fq>*>(wsum), Wh, c, reinterpret_cast<xyzz_t<Fq>*>(out));
-        else k_msm_combine<F><<<1, 32, 0, st>>>(wsum, W, c, out);
+        else k_msm_combine<F><<<1, 32, 0, st>>>(wsum, WB * wsplit, fold ? 0u : c, out);
     }
     return check_launch(ctx, "k_msm_combine");
 }
@@ -618,6 +632,55 @@ int msm_g1_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_sca
 int msm_g2_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n, void* d_out,
                cudaEvent_t bases_ready) {
     return msm_dev_impl<Fq2>(ctx, sl.stream, sl.ws_msm, d_bases, d_scalars, n, d_out, "msm_accumulate_g2", bases_ready);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 7. fixed-base window tables.  A proving key's query vectors never change between proofs, and a B200 has the HBM
+//    to keep table[w * n + i] = 2^{c w} * P_i for every digit window w: the digit (w, d) of scalar i then adds
+//    table[w * n + i] into bucket d of ONE bucket set -- no per-window bucket sets, no Horner doublings -- which lets
+//    c grow to ~log2(n) (13 bucket additions per scalar at c = 20 instead of 16) for the same reduction cost.
+// ---------------------------------------------------------------------------------------------
+unsigned msm_table_windows(unsigned c) { return (255 + c - 1) / c; }
+
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_table_build(const affine_t<F>* bases, uint32_t n, uint32_t c, uint32_t W,
+                                                         affine_t<F>* table) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    affine_t<F> p = ld16(bases + i);
+    st16(table + i, p);
+    for (uint32_t w = 1; w < W; ++w) {
+        if (!p.is_inf()) {
+            xyzz_t<F> acc = xyzz_t<F>::from_affine(p);
+            for (uint32_t k = 0; k < c; ++k) acc = xyzz_t<F>::dbl(acc);
+            p = xyzz_t<F>::to_affine(acc);
+        }
+        st16(table + (size_t)w * n + i, p);
+    }
+}
+
+template <class F>
+static int table_build_impl(b200zk_ctx* ctx, cudaStream_t st, const void* d_bases, size_t n, unsigned c, void* d_table) {
+    if (c < 2 || c > 24) return set_error(ctx, B200ZK_ERR_ARG, "table window must be in [2, 24]");
+    if (n == 0) return B200ZK_OK;
+    const unsigned W = msm_table_windows(c);
+    if ((uint64_t)W * n >= (1ull << 31)) return set_error(ctx, B200ZK_ERR_ARG, "table too large (W * n >= 2^31)");
+    {
+        LaunchScope ls(ctx, st, "msm_table_build");
+        k_msm_table_build<F><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(reinterpret_cast<const affine_t<F>*>(d_bases), (uint32_t)n,
+                                                                      c, W, reinterpret_cast<affine_t<F>*>(d_table));
+    }
+    return check_launch(ctx, "k_msm_table_build");
+}
+int msm_table_build_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_bases, size_t n, unsigned c, void* d_table) {
+    return g2 ? table_build_impl<Fq2>(ctx, sl.stream, d_bases, n, c, d_table)
+              : table_build_impl<Fq>(ctx, sl.stream, d_bases, n, c, d_table);
+}
+int msm_table_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_table, const void* d_scalars, size_t n, unsigned c,
+                  void* d_out) {
+    if (c < 2 || c > 24) return set_error(ctx, B200ZK_ERR_ARG, "table window must be in [2, 24]");
+    return g2 ? msm_dev_impl<Fq2>(ctx, sl.stream, sl.ws_msm, d_table, d_scalars, n, d_out, "msm_accumulate_g2", nullptr, nullptr, c)
+              : msm_dev_impl<Fq>(ctx, sl.stream, sl.ws_msm, d_table, d_scalars, n, d_out, "msm_accumulate_g1", nullptr, nullptr, c);
 }
 
 // Host-staged G1 MSM in two halves on two streams: the H2D copy of the second half and the latency-bound tail of the

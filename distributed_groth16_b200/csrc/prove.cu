@@ -103,6 +103,57 @@ __global__ void k_prove_finalize(FinalizeArgs f) {
 // 0/1/2 concurrently, prove.rs:119-125): slot 0 = h pipeline then MSM(h_query, h); slot 1 = the G2 MSM;
 // slot 2 = MSM(a_query) then MSM(l_query) (then MSM(b_g1_query)).  The latency-bound tails of one MSM
 // (bucket reduction, Horner) then overlap the throughput-bound bucket accumulation of another.
+void pk_free_tables(b200zk_pk* pk) {
+    for (int k = 0; k < 5; ++k) {
+        if (pk->tab[k]) cudaFree(pk->tab[k]);
+        pk->tab[k] = nullptr;
+        pk->tab_c[k] = 0;
+    }
+    pk->tab_bytes = 0;
+}
+
+// Window tables for the five query vectors (msm.cu section 7).  c = 0: ceil(log2 n) clamped to [10, 20] per query
+// (B200ZK_PK_TABLE_WINDOW overrides).  Skipped as a whole -- the generic MSM keeps running on the queries -- when
+// the tables would exceed B200ZK_PK_TABLE_MAX_GB (default 48) or the allocation fails.
+int pk_precompute_dev(b200zk_ctx* ctx, b200zk_pk* pk, unsigned c_req) {
+    pk_free_tables(pk);
+    Slot& sl = ctx->slots[0];
+    const size_t n1 = pk->n_vars - 1, n_aux = pk->n_vars - pk->n_inputs;
+    const void* src[5] = {(const char*)pk->a_query + 64, (const char*)pk->b_g1_query + 64, (const char*)pk->b_g2_query + 128,
+                          pk->l_query, pk->h_query};
+    const size_t cnt[5] = {n1, n1, n1, n_aux, pk->m};
+    const size_t psz[5] = {64, 64, 128, 64, 64};
+    if (const char* env = getenv("B200ZK_PK_TABLE_WINDOW")) { int v = atoi(env); if (v >= 2 && v <= 24) c_req = (unsigned)v; }
+    double max_gb = 48.0;
+    if (const char* env = getenv("B200ZK_PK_TABLE_MAX_GB")) max_gb = atof(env);
+    unsigned cs[5];
+    size_t total = 0;
+    for (int k = 0; k < 5; ++k) {
+        unsigned c = c_req ? c_req : ceil_log2(cnt[k] < 2 ? 2 : cnt[k]);
+        if (!c_req) c = c < 10 ? 10 : (c > 20 ? 20 : c);
+        cs[k] = c;
+        if ((uint64_t)msm_table_windows(c) * cnt[k] >= (1ull << 31)) return B200ZK_OK;       // generic path keeps working
+        total += (size_t)msm_table_windows(c) * cnt[k] * psz[k];
+    }
+    if ((double)total > max_gb * 1073741824.0) return B200ZK_OK;
+    for (int k = 0; k < 5; ++k) {
+        if (cnt[k] < 64) continue;                   // tiny query: nothing to gain
+        size_t bytes = (size_t)msm_table_windows(cs[k]) * cnt[k] * psz[k];
+        if (cudaMalloc(&pk->tab[k], bytes) != cudaSuccess) {
+            cudaGetLastError();
+            pk->tab[k] = nullptr;
+            pk_free_tables(pk);
+            return B200ZK_OK;
+        }
+        int rc = msm_table_build_dev(ctx, sl, k == 2, src[k], cnt[k], cs[k], pk->tab[k]);
+        if (rc) { pk_free_tables(pk); return rc; }
+        pk->tab_c[k] = cs[k];
+        pk->tab_bytes += bytes;
+    }
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(sl.stream));
+    return B200ZK_OK;
+}
+
 int prove_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, const Fr* d_a, const Fr* d_b, const Fr* d_c,
               const uint64_t r[4], const uint64_t s[4], int mirror_bg1, uint8_t proof_out[128]) {
     Slot& s0 = ctx->slots[0];
@@ -138,12 +189,17 @@ int prove_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, const Fr* d_a
     const char* aq = reinterpret_cast<const char*>(pk->a_query);
     const char* b1q = reinterpret_cast<const char*>(pk->b_g1_query);
     const char* b2q = reinterpret_cast<const char*>(pk->b_g2_query);
-    int rc = msm_g2_dev(ctx, s1, b2q + 128, d_z + 1, n1, sm + o_b2);
-    if (!rc) rc = msm_g1_dev(ctx, s2, aq + 64, d_z + 1, n1, sm + o_a);
-    if (!rc) rc = msm_g1_dev(ctx, s2, pk->l_query, d_z + pk->n_inputs, n_aux, sm + o_l);
-    if (!rc && need_b1) rc = msm_g1_dev(ctx, s2, b1q + 64, d_z + 1, n1, sm + o_b1);
+    // query k of the key: its fixed-base table when pk_precompute_dev built one, else the generic MSM on the query
+    auto msm = [&](Slot& sl, int k, int g2, const void* query, const Fr* scalars, size_t n, void* out) -> int {
+        if (pk->tab_c[k]) return msm_table_dev(ctx, sl, g2, pk->tab[k], scalars, n, pk->tab_c[k], out);
+        return g2 ? msm_g2_dev(ctx, sl, query, scalars, n, out) : msm_g1_dev(ctx, sl, query, scalars, n, out);
+    };
+    int rc = msm(s1, 2, 1, b2q + 128, d_z + 1, n1, sm + o_b2);
+    if (!rc) rc = msm(s2, 0, 0, aq + 64, d_z + 1, n1, sm + o_a);
+    if (!rc) rc = msm(s2, 3, 0, pk->l_query, d_z + pk->n_inputs, n_aux, sm + o_l);
+    if (!rc && need_b1) rc = msm(s2, 1, 0, b1q + 64, d_z + 1, n1, sm + o_b1);
     if (!rc) rc = h_circom_dev(ctx, s0, d_a, d_b, d_c, log_m, d_h);
-    if (!rc) rc = msm_g1_dev(ctx, s0, pk->h_query, d_h, m, sm + o_h);
+    if (!rc) rc = msm(s0, 4, 0, pk->h_query, d_h, m, sm + o_h);
     cudaEventRecord(ev1, s1.stream);
     cudaEventRecord(ev2, s2.stream);
     cudaStreamWaitEvent(st, ev1, 0);

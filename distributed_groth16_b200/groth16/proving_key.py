@@ -52,6 +52,17 @@ class ProvingKey:
         self._h = h
         return self
 
+    def precompute(self, c: int = 0):
+        """(Re)build the fixed-base window tables of the five query vectors (b200zk_pk_precompute): c = 0 -> automatic
+        window per query; c = None -> drop the tables, proving then runs the generic MSM on the queries.  The upload
+        already did precompute(0) unless B200ZK_PK_TABLES=0.  Proof bytes are identical either way."""
+        self.net.check(self.net._lib.b200zk_pk_precompute(self.net._h, self._h, 0xFFFFFFFF if c is None else int(c)))
+        return self.table_bytes
+
+    @property
+    def table_bytes(self) -> int:
+        return int(self.net._lib.b200zk_pk_table_bytes(self._h))
+
     def free(self):
         if getattr(self, "_h", None) and self.net._h:
             self.net._lib.b200zk_pk_free(self.net._h, self._h)

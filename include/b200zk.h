@@ -69,6 +69,16 @@ int b200zk_msm_g1_dev(b200zk_ctx* ctx, int stream, const void* d_bases, const vo
                       void* d_out_xyzz);
 int b200zk_msm_g2_dev(b200zk_ctx* ctx, int stream, const void* d_bases, const void* d_scalars, size_t n,
                       void* d_out_xyzz);
+/* Fixed-base window tables: for bases that never change between calls (the proving key's query vectors,
+ * groth16/src/proving_key.rs:35-110) keep table[w * n + i] = 2^{c w} * bases[i], w < b200zk_msm_table_windows(c) =
+ * ceil(255 / c), resident in HBM.  b200zk_msm_table_dev then computes the same sum as b200zk_msm_g{1,2}_dev with one
+ * bucket set and no doublings (g2 = 0: G1, 64-byte points; 1: G2, 128-byte points).  d_table must hold
+ * windows * n points. */
+unsigned b200zk_msm_table_windows(unsigned c);
+int b200zk_msm_table_build_dev(b200zk_ctx* ctx, int stream, int g2, const void* d_bases, size_t n, unsigned c,
+                               void* d_table);
+int b200zk_msm_table_dev(b200zk_ctx* ctx, int stream, int g2, const void* d_table, const void* d_scalars, size_t n,
+                         unsigned c, void* d_out_xyzz);
 /* Sum `count` XYZZ partials (device) and normalise to affine (host). */
 int b200zk_g1_sum_dev(b200zk_ctx* ctx, int stream, const void* d_xyzz, size_t count, uint64_t out_affine[8],
                       int* out_is_inf);
@@ -147,6 +157,13 @@ int b200zk_pk_upload_dev(b200zk_ctx* ctx, const void* d_a_query, const void* d_b
                          const void* d_l_query, const void* d_h_query, size_t n_vars, size_t n_inputs, size_t m,
                          const uint64_t* vk_points, b200zk_pk** out);
 void b200zk_pk_free(b200zk_ctx* ctx, b200zk_pk* pk);
+/* (Re)build the key's fixed-base window tables (b200zk_msm_table_*): c = 0 picks ceil(log2 n) clamped to [10, 20]
+ * per query, c = 0xFFFFFFFF drops the tables.  b200zk_pk_upload{,_dev} call this with c = 0 unless the environment
+ * has B200ZK_PK_TABLES=0; tables that would exceed B200ZK_PK_TABLE_MAX_GB (default 48) are skipped and proving runs
+ * the generic MSM on the queries.  The proof bytes do not depend on the choice.  b200zk_pk_table_bytes: HBM held by
+ * the tables (0 = none). */
+int b200zk_pk_precompute(b200zk_ctx* ctx, b200zk_pk* pk, unsigned c);
+size_t b200zk_pk_table_bytes(const b200zk_pk* pk);
 
 /* ---- prove::{A,B,C}::compute + assembly (groth16/src/prove.rs:21-136, examples/sha256.rs:208-212)
  * z: full assignment (n_vars x 4 limbs, z[0] = 1); a, b, c: QAP evaluation vectors (m x 4 limbs);

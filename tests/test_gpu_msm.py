@@ -140,3 +140,45 @@ def test_larger_sizes_2_22_vs_oracle_and_2_24_linearity(net, cref):
     both = np.stack([a.limbs, b.limbs])
     exp_sum, _ = cref.msm_g1(both, layout.fr_to_arr([1, 1]))
     assert (c.limbs == exp_sum).all() and not c.infinity
+
+
+@pytest.mark.parametrize("g2", [False, True])
+@pytest.mark.parametrize("n,c", [(1, 9), (37, 4), (3000, 8), (3000, 13), (20000, 15)])
+def test_fixed_base_tables_give_the_same_point(net, cref, n, c, g2):
+    """b200zk_msm_table_* (one bucket set over 2^{cw} P_i tables) vs the oracle, edge cases included."""
+    import torch
+    from oracle import layout, bn254 as o
+    bases = (cref.g2_generate if g2 else cref.g1_generate)(0xB2000007 + c, n)
+    scalars = cref.fr_generate(0xB2000008 + n, n)
+    if n >= 37:
+        scalars[:6] = layout.fr_to_arr([0, 1, o.R - 1, 1 << 253, (1 << 253) + (1 << 252) - 1, 5])
+        bases[7] = 0                                      # infinity base stays infinity in every window
+        bases[9] = bases[10]
+        scalars[9] = scalars[10]                          # equal points meet in every bucket they share
+    db = torch.from_numpy(bases.view(np.int64)).cuda()
+    ds = torch.from_numpy(scalars.view(np.int64)).cuda()
+    table = net.msm_table_build(db, c, g2=g2)
+    w = net.msm_table_windows(c)
+    assert w == -(-255 // c) and table.shape[0] == w * n
+    assert (table[:n].cpu().numpy().view(np.uint64) == bases).all()
+    if not g2 and n >= 37:                                # window 1 of point 0 = 2^c * P_0
+        exp1, _ = cref.msm_g1(bases[:1], layout.fr_to_arr([1 << c]))
+        assert (table[n].cpu().numpy().view(np.uint64) == exp1).all()
+        assert not table[n + 7].any() and not table[(w - 1) * n + 7].any()
+    part = net.msm_table_dev(table, ds, c, g2=g2)
+    got, inf = net.sum_points_dev(part, 1, g2=g2)
+    exp, einf = (cref.msm_g2 if g2 else cref.msm_g1)(bases, scalars)
+    assert inf == einf and (got == exp).all()
+    with pytest.raises(MpcNetError):
+        net.msm_table_dev(table, ds[: n - 1] if n > 1 else ds[:0], c, g2=g2)
+
+
+def test_fixed_base_tables_2_20_match_generic_path(net):
+    """BASELINE config 2 size: table path == generic path (both normalised), c = 20 as the proving key picks."""
+    n = 1 << 20
+    bases = net.generate_g1(0xB2000002, n)
+    scalars = net.generate_fr(0xB2000002, n)
+    a, ainf = net.sum_points_dev(net.msm_dev(bases, scalars), 1)
+    table = net.msm_table_build(bases, 20)
+    b, binf = net.sum_points_dev(net.msm_table_dev(table, scalars, 20), 1)
+    assert not ainf and not binf and (a == b).all()

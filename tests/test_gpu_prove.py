@@ -54,6 +54,25 @@ def test_prove_bytes_match_oracle(net, cref, rs, mirror):
     pk.free()
 
 
+def test_prove_bytes_do_not_depend_on_the_fixed_base_tables(net, cref):
+    """The key's window tables (b200zk_pk_precompute) are an HBM-for-time trade: same 128 bytes with automatic
+    windows, a forced small window, and no tables at all."""
+    from oracle import layout
+    m, n_vars, n_inputs = 1 << 11, 2500, 3
+    aq, b1, b2, lq, hq, vk1, vk2, z, a, b, c = _dummy_instance(cref, m, n_vars, n_inputs, 300)
+    r, s = layout.fr_to_arr([777])[0], layout.fr_to_arr([999])[0]
+    vk = np.concatenate([vk1.reshape(-1), vk2.reshape(-1)])
+    exp = cref.groth16_prove(aq, b1, b2, lq, hq, vk, n_inputs, z, cref.h_circom(a, b, c), r, s, mirror_bg1=False)
+    pk = ProvingKey(net, aq, b1, b2, lq, hq, n_inputs, vk1[0], vk1[1], vk1[2], vk2[0], vk2[1])
+    assert pk.table_bytes > 0                              # built by the upload
+    assert prove.create_proof(pk, z, a, b, c, r, s) == exp
+    assert pk.precompute(7) > 0
+    assert prove.create_proof(pk, z, a, b, c, r, s) == exp
+    assert pk.precompute(None) == 0
+    assert prove.create_proof(pk, z, a, b, c, r, s) == exp
+    pk.free()
+
+
 def test_prove_structs_mirror_reference_call_pattern(net, cref):
     """groth16/examples/sha256.rs:45-88 + :208-212 with r = s = 0, assembled from A/B/C structs."""
     from oracle import layout

@@ -47,7 +47,8 @@ def main():
     assert proof == proof2
     out = {"log_m": log_m, "prove_ms": sorted(times[1:])[len(times[1:]) // 2], "prove_ms_all": times,
            "kernel_ms": {k: round(v["ms"], 3) for k, v in rep.items()}, "launches": sum(v["launches"] for v in rep.values())}
-    print("prove 2^%d: %.2f ms (runs %s)" % (log_m, out["prove_ms"], ["%.1f" % t for t in times]))
+    out["pk_table_gb"] = pk.table_bytes / 2**30
+    print("prove 2^%d: %.2f ms (runs %s)  pk tables %.2f GB" % (log_m, out["prove_ms"], ["%.1f" % t for t in times], out["pk_table_gb"]))
     print("  kernels:", out["kernel_ms"])
     if check:
         from oracle import cref
