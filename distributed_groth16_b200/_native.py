@@ -45,6 +45,7 @@ SIGNATURES = {
     "b200zk_msm_g1_dev": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "b200zk_msm_g2_dev": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "b200zk_msm_table_windows": (ctypes.c_uint, [ctypes.c_uint]),
+    "b200zk_msm_table_auto_window": (ctypes.c_uint, [ctypes.c_size_t]),
     "b200zk_msm_table_build_dev": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_size_t, ctypes.c_uint, c_vp]),
     "b200zk_msm_table_dev": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp, ctypes.c_size_t, ctypes.c_uint, c_vp]),
     "b200zk_g1_sum_dev": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, ctypes.c_size_t, c_vp, ctypes.POINTER(ctypes.c_int)]),

@@ -196,6 +196,9 @@ class Net:
     def msm_table_windows(self, c: int) -> int:
         return int(self._lib.b200zk_msm_table_windows(int(c)))
 
+    def msm_table_auto_window(self, n: int) -> int:
+        return int(self._lib.b200zk_msm_table_auto_window(int(n)))
+
     def msm_table_build(self, bases, c: int, g2: bool = False, sid: int = 0):
         """Fixed-base window table of `bases` (CUDA int64, n x 8 / n x 16): (windows * n) points, table[w*n+i] =
         2^{c w} * bases[i].  For bases that stay resident across calls (a proving key's query vectors)."""

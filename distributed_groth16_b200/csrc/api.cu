@@ -256,6 +256,7 @@ int b200zk_msm_g2_dev(b200zk_ctx* ctx, int stream, const void* d_bases, const vo
 }
 
 unsigned b200zk_msm_table_windows(unsigned c) { return c ? msm_table_windows(c) : 0; }
+unsigned b200zk_msm_table_auto_window(size_t n) { return msm_table_auto_window(n); }
 int b200zk_msm_table_build_dev(b200zk_ctx* ctx, int stream, int g2, const void* d_bases, size_t n, unsigned c, void* d_table) {
     if (!ctx || !valid_slot(stream) || (n && (!d_bases || !d_table))) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[stream];

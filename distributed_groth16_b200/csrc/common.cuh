@@ -177,6 +177,7 @@ int msm_g2_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_sca
 int msm_g1_two_halves_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n1, size_t n2,
                           cudaEvent_t ev[4], void* d_out2);
 unsigned msm_table_windows(unsigned c);
+unsigned msm_table_auto_window(size_t n);
 int msm_table_build_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_bases, size_t n, unsigned c, void* d_table);
 int msm_table_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_table, const void* d_scalars, size_t n, unsigned c,
                   void* d_out_xyzz);

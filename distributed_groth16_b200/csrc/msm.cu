@@ -200,79 +200,85 @@ __global__ void k_msm_scatter(const uint32_t* keys, const uint32_t* ranks, const
 //    serialising one.  Single-task buckets write their sum straight into buckets[g]; the rare
 //    multi-task buckets go through task_sums[] and a block-level merge.
 // ---------------------------------------------------------------------------------------------
-static const uint32_t TASK_LEN = 128;
+static const uint32_t TASK_LEN = 128, MAX_TASK_LEN = 1024;    // default / largest task length (runtime: task_len)
 #ifndef B2_ACC_MINBLOCKS
 #define B2_ACC_MINBLOCKS 4
 #endif
 #ifndef B2_ACC_MINBLOCKS_G2
-#define B2_ACC_MINBLOCKS_G2 2
+#define B2_ACC_MINBLOCKS_G2 4
 #endif
 
-__global__ void k_msm_task_counts(const uint32_t* offsets, uint32_t nbuckets, uint32_t* ntasks) {
+__global__ void k_msm_task_counts(const uint32_t* offsets, uint32_t nbuckets, uint32_t task_len, uint32_t* ntasks) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g > nbuckets) return;
-    ntasks[g] = g < nbuckets ? (offsets[g + 1] - offsets[g] + TASK_LEN - 1) / TASK_LEN : 0;
+    ntasks[g] = g < nbuckets ? (offsets[g + 1] - offsets[g] + task_len - 1) / task_len : 0;
 }
 
-// task_bucket[t] = owning bucket; buckets with > 1 task are appended to multi_list
+// task_bucket[t] = owning bucket; buckets with > 1 task are appended to multi_list from the front when they have more
+// than MERGE_SMALL tasks (block-level merge) and from the back otherwise (one thread each); counts[0] / counts[1]
+static const uint32_t MERGE_SMALL = 8;
 __global__ void k_msm_fill_tasks(const uint32_t* task_off, uint32_t nbuckets, uint32_t* task_bucket, uint32_t* multi_list,
-                                 uint32_t* multi_count) {
+                                 uint32_t list_cap, uint32_t* multi_count) {
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= nbuckets) return;
     uint32_t lo = task_off[g], hi = task_off[g + 1];
     for (uint32_t t = lo; t < hi; ++t) task_bucket[t] = g;
-    if (hi - lo > 1) multi_list[atomicAdd(multi_count, 1u)] = g;
+    if (hi - lo > MERGE_SMALL) multi_list[atomicAdd(multi_count, 1u)] = g;
+    else if (hi - lo > 1) multi_list[list_cap - 1 - atomicAdd(multi_count + 1, 1u)] = g;
 }
 
 // Counting sort of the tasks by length (descending): the lanes of a warp then run loops of (almost)
 // equal length.  Unsorted, bucket sizes ~Poisson(32) leave only 23 of 32 lanes active on average
 // (ncu smsp__thread_inst_executed_per_inst_executed, profiles/r1a_full.md).
-__device__ __forceinline__ uint32_t task_length(const uint32_t* offsets, const uint32_t* task_off, uint32_t g, uint32_t t) {
-    uint32_t lo = offsets[g] + (t - task_off[g]) * TASK_LEN, end = offsets[g + 1];
-    return (lo + TASK_LEN < end ? lo + TASK_LEN : end) - lo;
+__device__ __forceinline__ uint32_t task_length(const uint32_t* offsets, const uint32_t* task_off, uint32_t g, uint32_t t,
+                                                uint32_t task_len) {
+    uint32_t lo = offsets[g] + (t - task_off[g]) * task_len, end = offsets[g + 1];
+    return (lo + task_len < end ? lo + task_len : end) - lo;
 }
 __global__ void __launch_bounds__(256) k_msm_task_hist(const uint32_t* offsets, const uint32_t* task_off, const uint32_t* task_bucket,
-                                uint32_t nbuckets, uint32_t* hist, uint32_t* task_rank) {
-    __shared__ uint32_t sh_cnt[TASK_LEN + 1], sh_base[TASK_LEN + 1];     // block-local histogram first:
-    for (uint32_t i = threadIdx.x; i <= TASK_LEN; i += blockDim.x) sh_cnt[i] = 0;   // few hot bins -> keep contention in smem
+                                uint32_t nbuckets, uint32_t task_len, uint32_t* hist, uint32_t* task_rank) {
+    __shared__ uint32_t sh_cnt[MAX_TASK_LEN + 1], sh_base[MAX_TASK_LEN + 1];     // block-local histogram first:
+    for (uint32_t i = threadIdx.x; i <= task_len; i += blockDim.x) sh_cnt[i] = 0;   // few hot bins -> keep contention in smem
     __syncthreads();
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     bool live = t < task_off[nbuckets];
     uint32_t len = 0, local = 0;
     if (live) {
-        len = task_length(offsets, task_off, task_bucket[t], t);
+        len = task_length(offsets, task_off, task_bucket[t], t, task_len);
         local = atomicAdd(sh_cnt + len, 1u);
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i <= TASK_LEN; i += blockDim.x)
+    for (uint32_t i = threadIdx.x; i <= task_len; i += blockDim.x)
         if (sh_cnt[i]) sh_base[i] = atomicAdd(hist + i, sh_cnt[i]);
     __syncthreads();
     if (live) task_rank[t] = sh_base[len] + local;
 }
-__global__ void k_msm_task_hist_scan(uint32_t* hist) {      // base[len] = #tasks longer than len; 1 thread
+__global__ void k_msm_task_hist_scan(uint32_t* hist, uint32_t task_len) {      // base[len] = #tasks longer than len; 1 thread
     uint32_t run = 0;
-    for (int len = (int)TASK_LEN; len >= 0; --len) { uint32_t c = hist[len]; hist[len] = run; run += c; }
+    for (int len = (int)task_len; len >= 0; --len) { uint32_t c = hist[len]; hist[len] = run; run += c; }
 }
 __global__ void k_msm_task_order(const uint32_t* offsets, const uint32_t* task_off, const uint32_t* task_bucket,
-                                 uint32_t nbuckets, const uint32_t* hist, const uint32_t* task_rank, uint32_t* order) {
+                                 uint32_t nbuckets, uint32_t task_len, const uint32_t* hist, const uint32_t* task_rank,
+                                 uint32_t* order) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= task_off[nbuckets]) return;
-    uint32_t len = task_length(offsets, task_off, task_bucket[t], t);
+    uint32_t len = task_length(offsets, task_off, task_bucket[t], t, task_len);
     order[hist[len] + task_rank[t]] = t;
 }
 
-// G2 (Fq2 coordinates) needs ~2x the registers of G1: capping it at 128 spilled 1.1 KB/thread to local memory
+// G2 (Fq2 coordinates): 250 registers uncapped = 8 warps/SM, fmaheavy 74% busy with `wait` the top stall
+// (profiles/r1c_g2_accumulate.md); capped at 128 (4 blocks/SM, some spills) it measures 8.29 vs 8.89 ms at 2^20; 5+ blocks lose again
 template <class F>
 __global__ void __launch_bounds__(128, sizeof(F) > 32 ? B2_ACC_MINBLOCKS_G2 : B2_ACC_MINBLOCKS) k_msm_accumulate(const affine_t<F>* bases, const uint32_t* entries, const uint32_t* offsets,
                                  const uint32_t* task_off, const uint32_t* task_bucket, const uint32_t* order,
-                                 uint32_t nbuckets, xyzz_t<F>* buckets, xyzz_t<F>* task_sums) {
+                                 uint32_t nbuckets, uint32_t task_len, xyzz_t<F>* buckets, xyzz_t<F>* task_sums) {
     uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= task_off[nbuckets]) return;
     uint32_t t = order[tid];
     uint32_t g = task_bucket[t];
     uint32_t t0 = task_off[g], nt = task_off[g + 1] - t0;
-    uint32_t lo = offsets[g] + (t - t0) * TASK_LEN, end = offsets[g + 1];
-    uint32_t hi = lo + TASK_LEN < end ? lo + TASK_LEN : end;
+    uint32_t lo = offsets[g] + (t - t0) * task_len, end = offsets[g + 1];
+    uint32_t hi = lo + task_len < end ? lo + task_len : end;
     xyzz_t<F> acc = xyzz_t<F>::identity();
     for (uint32_t k = lo; k < hi; ++k) {
         uint32_t e = entries[k];
@@ -311,6 +317,20 @@ __global__ void __launch_bounds__(128) k_msm_merge_tasks(const uint32_t* multi_l
         }
         if (threadIdx.x == 0) st16(buckets + g, sh[0]);
         __syncthreads();
+    }
+}
+
+// the buckets with 2..MERGE_SMALL tasks (n >> 2^c: most of them): one thread per bucket
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_merge_small(const uint32_t* multi_list, uint32_t list_cap, const uint32_t* small_count,
+                                                         const uint32_t* task_off, const xyzz_t<F>* task_sums, xyzz_t<F>* buckets) {
+    uint32_t cnt = *small_count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+        uint32_t g = multi_list[list_cap - 1 - i];
+        uint32_t lo = task_off[g], hi = task_off[g + 1];
+        xyzz_t<F> acc = ld16(task_sums + lo);
+        for (uint32_t t = lo + 1; t < hi; ++t) acc = add_sel<F>(acc, ld16(task_sums + t));
+        st16(buckets + g, acc);
     }
 }
 
@@ -493,13 +513,20 @@ static int msm_dev_impl(b200zk_ctx* ctx, cudaStream_t st, DevBuf& ws_buf, const 
     size_t o_counts = o_entries + al(total * 4);
     size_t o_offsets = o_counts + al(((size_t)nb + 1) * 4);
     size_t o_sums = o_offsets + al(((size_t)nb + 1) * 4);
-    const size_t max_tasks = total / TASK_LEN + nb + 1;
+    // task length: 128 unless the average bucket is already that long (n >> 2^c: every bucket would be cut in two);
+    // then the next power of two above 3x the average -- only outliers are split -- as long as that leaves enough
+    // tasks (>= 2^19) to fill the machine
+    uint32_t task_len = TASK_LEN;
+    while (task_len < MAX_TASK_LEN && (uint64_t)task_len * nb < 3 * (uint64_t)total &&
+           total / (2 * task_len) + nb >= (1u << 19))
+        task_len *= 2;
+    const size_t max_tasks = total / task_len + nb + 1;
     size_t o_ntasks = o_sums + al(((size_t)nb / SCAN_TILE + 2) * 4);
     size_t o_taskoff = o_ntasks + al(((size_t)nb + 1) * 4);
     size_t o_taskbucket = o_taskoff + al(((size_t)nb + 1) * 4);
     size_t o_multi = o_taskbucket + al(max_tasks * 4);
-    size_t o_hist = o_multi + al((total / TASK_LEN + 2) * 4);
-    size_t o_rank = o_hist + al((TASK_LEN + 1) * 4);
+    size_t o_hist = o_multi + al((total / task_len + 4) * 4);
+    size_t o_rank = o_hist + al((MAX_TASK_LEN + 1) * 4);
     size_t o_order = o_rank + al(max_tasks * 4);
     size_t o_tasksums = o_order + al(max_tasks * 4);
     size_t o_buckets = o_tasksums + al(max_tasks * sizeof(xyzz_t<F>));
@@ -517,7 +544,8 @@ static int msm_dev_impl(b200zk_ctx* ctx, cudaStream_t st, DevBuf& ws_buf, const 
     uint32_t* ntasks = reinterpret_cast<uint32_t*>(ws + o_ntasks);
     uint32_t* task_off = reinterpret_cast<uint32_t*>(ws + o_taskoff);
     uint32_t* task_bucket = reinterpret_cast<uint32_t*>(ws + o_taskbucket);
-    uint32_t* multi = reinterpret_cast<uint32_t*>(ws + o_multi);       // [0] = count, [1..] = list
+    uint32_t* multi = reinterpret_cast<uint32_t*>(ws + o_multi);       // [0], [1] = big / small counts, [2..] = list
+    const uint32_t list_cap = (uint32_t)(total / task_len + 1);
     uint32_t* hist = reinterpret_cast<uint32_t*>(ws + o_hist);
     uint32_t* task_rank = reinterpret_cast<uint32_t*>(ws + o_rank);
     uint32_t* order = reinterpret_cast<uint32_t*>(ws + o_order);
@@ -538,29 +566,29 @@ static int msm_dev_impl(b200zk_ctx* ctx, cudaStream_t st, DevBuf& ws_buf, const 
     B2_TRY(exclusive_scan(ctx, st, counts, offsets, sums, nb + 1));
     {
         LaunchScope ls(ctx, st, "msm_tasks");
-        k_msm_task_counts<<<(nb + 1 + 255) / 256, 256, 0, st>>>(offsets, nb, ntasks);
+        k_msm_task_counts<<<(nb + 1 + 255) / 256, 256, 0, st>>>(offsets, nb, task_len, ntasks);
     }
     B2_TRY(check_launch(ctx, "k_msm_task_counts"));
     B2_TRY(exclusive_scan(ctx, st, ntasks, task_off, sums, nb + 1));
-    B2_CUDA_OK(ctx, cudaMemsetAsync(multi, 0, 4, st));
+    B2_CUDA_OK(ctx, cudaMemsetAsync(multi, 0, 8, st));
     B2_CUDA_OK(ctx, cudaMemsetAsync(buckets, 0, (size_t)nb * sizeof(xyzz_t<F>), st));   // all-zero XYZZ = identity
     {
         LaunchScope ls(ctx, st, "msm_tasks");
-        k_msm_fill_tasks<<<(nb + 255) / 256, 256, 0, st>>>(task_off, nb, task_bucket, multi + 1, multi);
+        k_msm_fill_tasks<<<(nb + 255) / 256, 256, 0, st>>>(task_off, nb, task_bucket, multi + 2, list_cap, multi);
     }
     B2_TRY(check_launch(ctx, "k_msm_fill_tasks"));
-    B2_CUDA_OK(ctx, cudaMemsetAsync(hist, 0, (TASK_LEN + 1) * 4, st));
+    B2_CUDA_OK(ctx, cudaMemsetAsync(hist, 0, (MAX_TASK_LEN + 1) * 4, st));
     {
         LaunchScope ls(ctx, st, "msm_tasks");
-        k_msm_task_hist<<<(unsigned)((max_tasks + 255) / 256), 256, 0, st>>>(offsets, task_off, task_bucket, nb, hist, task_rank);
+        k_msm_task_hist<<<(unsigned)((max_tasks + 255) / 256), 256, 0, st>>>(offsets, task_off, task_bucket, nb, task_len, hist, task_rank);
     }
     {
         LaunchScope ls(ctx, st, "msm_tasks");
-        k_msm_task_hist_scan<<<1, 1, 0, st>>>(hist);
+        k_msm_task_hist_scan<<<1, 1, 0, st>>>(hist, task_len);
     }
     {
         LaunchScope ls(ctx, st, "msm_tasks");
-        k_msm_task_order<<<(unsigned)((max_tasks + 255) / 256), 256, 0, st>>>(offsets, task_off, task_bucket, nb, hist, task_rank, order);
+        k_msm_task_order<<<(unsigned)((max_tasks + 255) / 256), 256, 0, st>>>(offsets, task_off, task_bucket, nb, task_len, hist, task_rank, order);
     }
     B2_TRY(check_launch(ctx, "k_msm_task_order"));
     {
@@ -589,7 +617,7 @@ static int msm_dev_impl(b200zk_ctx* ctx, cudaStream_t st, DevBuf& ws_buf, const 
     {
         LaunchScope ls(ctx, st, acc_name);
         k_msm_accumulate<F><<<(unsigned)((max_tasks + 127) / 128), 128, 0, st>>>(
-            reinterpret_cast<const affine_t<F>*>(d_bases), entries, offsets, task_off, task_bucket, order, nb, buckets, task_sums);
+            reinterpret_cast<const affine_t<F>*>(d_bases), entries, offsets, task_off, task_bucket, order, nb, task_len, buckets, task_sums);
     }
     B2_TRY(check_launch(ctx, "k_msm_accumulate"));
     if (l2_window) {
@@ -601,7 +629,11 @@ static int msm_dev_impl(b200zk_ctx* ctx, cudaStream_t st, DevBuf& ws_buf, const 
     }
     {
         LaunchScope ls(ctx, st, "msm_merge");
-        k_msm_merge_tasks<F><<<2 * ctx->sm_count, 128, 0, st>>>(multi + 1, multi, task_off, task_sums, buckets);
+        k_msm_merge_tasks<F><<<2 * ctx->sm_count, 128, 0, st>>>(multi + 2, multi, task_off, task_sums, buckets);
+    }
+    {
+        LaunchScope ls(ctx, st, "msm_merge");
+        k_msm_merge_small<F><<<4 * ctx->sm_count, 128, 0, st>>>(multi + 2, list_cap, multi + 1, task_off, task_sums, buckets);
     }
     B2_TRY(check_launch(ctx, "k_msm_merge_tasks"));
     {
@@ -641,6 +673,20 @@ int msm_g2_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_sca
 //    c grow to ~log2(n) (13 bucket additions per scalar at c = 20 instead of 16) for the same reduction cost.
 // ---------------------------------------------------------------------------------------------
 unsigned msm_table_windows(unsigned c) { return (255 + c - 1) / c; }
+// Window for n fixed bases: about log2(n) (the bucket reduction then costs what the 13-17 additions per scalar save),
+// in [10, 20], preferring a c whose top digit window still has >= 6 bits: a 2-3 bit top window sends n / 4 entries
+// to each of a handful of buckets, which serialises the histogram atomics of k_msm_digits (c = 18: 0.37 vs 0.13 ms)
+unsigned msm_table_auto_window(size_t n) {
+    int L = (int)ceil_log2(n < 2 ? 2 : n);
+    L = L < 10 ? 10 : (L > 20 ? 20 : L);
+    const int cand[4] = {L, L - 1, L + 1, L - 2};
+    for (int c : cand) {
+        if (c < 10 || c > 20) continue;
+        int top = 254 - ((int)msm_table_windows((unsigned)c) - 1) * c;
+        if (top >= 6) return (unsigned)c;
+    }
+    return (unsigned)L;
+}
 
 template <class F>
 __global__ void __launch_bounds__(128) k_msm_table_build(const affine_t<F>* bases, uint32_t n, uint32_t c, uint32_t W,

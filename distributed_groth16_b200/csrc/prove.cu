@@ -112,7 +112,7 @@ void pk_free_tables(b200zk_pk* pk) {
     pk->tab_bytes = 0;
 }
 
-// Window tables for the five query vectors (msm.cu section 7).  c = 0: ceil(log2 n) clamped to [10, 20] per query
+// Window tables for the five query vectors (msm.cu section 7).  c = 0: msm_table_auto_window(n) per query
 // (B200ZK_PK_TABLE_WINDOW overrides).  Skipped as a whole -- the generic MSM keeps running on the queries -- when
 // the tables would exceed B200ZK_PK_TABLE_MAX_GB (default 48) or the allocation fails.
 int pk_precompute_dev(b200zk_ctx* ctx, b200zk_pk* pk, unsigned c_req) {
@@ -129,9 +129,8 @@ int pk_precompute_dev(b200zk_ctx* ctx, b200zk_pk* pk, unsigned c_req) {
     unsigned cs[5];
     size_t total = 0;
     for (int k = 0; k < 5; ++k) {
-        unsigned c = c_req ? c_req : ceil_log2(cnt[k] < 2 ? 2 : cnt[k]);
-        if (!c_req) c = c < 10 ? 10 : (c > 20 ? 20 : c);
-        cs[k] = c;
+        cs[k] = c_req ? c_req : msm_table_auto_window(cnt[k]);
+        const unsigned c = cs[k];
         if ((uint64_t)msm_table_windows(c) * cnt[k] >= (1ull << 31)) return B200ZK_OK;       // generic path keeps working
         total += (size_t)msm_table_windows(c) * cnt[k] * psz[k];
     }

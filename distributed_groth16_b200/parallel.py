@@ -16,6 +16,7 @@ logic (index maps, collectives) can be exercised with the CPU oracle under gloo 
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 
@@ -169,11 +170,21 @@ class ShardedProvingKey:
     `sharded_h` (local[c][r] = h_query[r*ncols + c0 + c], flattened), so that it lines up with the h this rank
     computes.  vk_points: the 56 limbs of b200zk_pk_upload (replicated)."""
 
-    def __init__(self, net, a_query, b_g1_query, b_g2_query, l_query, h_query_cols, n_inputs, vk_points):
+    def __init__(self, net, a_query, b_g1_query, b_g2_query, l_query, h_query_cols, n_inputs, vk_points, tables=True):
         from .groth16.proving_key import ProvingKey
         self.net = net
         self.a_query, self.b_g1_query, self.b_g2_query = a_query, b_g1_query, b_g2_query
         self.l_query, self.h_query = l_query, h_query_cols.reshape(-1, 8)
+        # fixed-base window tables of this rank's slices (b200zk_msm_table_*; same policy as b200zk_pk_precompute)
+        self.tables = {}
+        if tables and os.environ.get("B200ZK_PK_TABLES", "1") != "0":
+            for name, g2 in (("a_query", False), ("b_g1_query", False), ("b_g2_query", True), ("l_query", False),
+                             ("h_query", False)):
+                q = getattr(self, name)
+                n = int(q.shape[0])
+                if n >= 64:
+                    c = net.msm_table_auto_window(n)
+                    self.tables[name] = (net.msm_table_build(q, c, g2=g2), c)
         # the device-side pk object is only used for query[0] / vk in the final assembly
         self.pk = ProvingKey.from_device(net, a_query[:1], b_g1_query[:1], b_g2_query[:1], a_query[:0], h_query_cols.reshape(-1, 8)[:1],
                                          1, vk_points)
@@ -202,12 +213,18 @@ def sharded_prove(net, spk: ShardedProvingKey, z_shard, z_aux_shard, a, b, c, lo
     dev = z_shard.device
     # slots: 0 A(G1) 1 L 2 H 3 B1 (each 16 words) then B2 (32 words)
     parts = torch.zeros(4 * 16 + 32, dtype=torch.int64, device=dev)
-    net.msm_dev(spk.a_query, z_shard, parts[0:16])
-    net.msm_dev(spk.l_query, z_aux_shard, parts[16:32])
-    net.msm_dev(spk.h_query, h, parts[32:48])
+    def msm(name, scalars, out, g2=False):
+        if name in spk.tables:
+            table, c = spk.tables[name]
+            net.msm_table_dev(table, scalars, c, out, g2=g2)
+        else:
+            net.msm_dev(getattr(spk, name), scalars, out, g2=g2)
+    msm("a_query", z_shard, parts[0:16])
+    msm("l_query", z_aux_shard, parts[16:32])
+    msm("h_query", h, parts[32:48])
     if need_b1:
-        net.msm_dev(spk.b_g1_query, z_shard, parts[48:64])
-    net.msm_dev(spk.b_g2_query, z_shard, parts[64:96], g2=True)
+        msm("b_g1_query", z_shard, parts[48:64])
+    msm("b_g2_query", z_shard, parts[64:96], g2=True)
     if world > 1:
         gathered = torch.empty((world, parts.numel()), dtype=parts.dtype, device=dev)
         dist.all_gather_into_tensor(gathered, parts.reshape(1, -1), group=group)

@@ -75,6 +75,8 @@ int b200zk_msm_g2_dev(b200zk_ctx* ctx, int stream, const void* d_bases, const vo
  * bucket set and no doublings (g2 = 0: G1, 64-byte points; 1: G2, 128-byte points).  d_table must hold
  * windows * n points. */
 unsigned b200zk_msm_table_windows(unsigned c);
+/* The window b200zk_pk_precompute picks for n bases (about log2 n, in [10, 20]). */
+unsigned b200zk_msm_table_auto_window(size_t n);
 int b200zk_msm_table_build_dev(b200zk_ctx* ctx, int stream, int g2, const void* d_bases, size_t n, unsigned c,
                                void* d_table);
 int b200zk_msm_table_dev(b200zk_ctx* ctx, int stream, int g2, const void* d_table, const void* d_scalars, size_t n,
@@ -157,7 +159,7 @@ int b200zk_pk_upload_dev(b200zk_ctx* ctx, const void* d_a_query, const void* d_b
                          const void* d_l_query, const void* d_h_query, size_t n_vars, size_t n_inputs, size_t m,
                          const uint64_t* vk_points, b200zk_pk** out);
 void b200zk_pk_free(b200zk_ctx* ctx, b200zk_pk* pk);
-/* (Re)build the key's fixed-base window tables (b200zk_msm_table_*): c = 0 picks ceil(log2 n) clamped to [10, 20]
+/* (Re)build the key's fixed-base window tables (b200zk_msm_table_*): c = 0 picks b200zk_msm_table_auto_window(n)
  * per query, c = 0xFFFFFFFF drops the tables.  b200zk_pk_upload{,_dev} call this with c = 0 unless the environment
  * has B200ZK_PK_TABLES=0; tables that would exceed B200ZK_PK_TABLE_MAX_GB (default 48) are skipped and proving runs
  * the generic MSM on the queries.  The proof bytes do not depend on the choice.  b200zk_pk_table_bytes: HBM held by

@@ -10,6 +10,8 @@ from distributed_groth16_b200 import build as b
 VARIANTS = {
     "g2_b3": ["B2_ACC_MINBLOCKS_G2=3"],
     "g2_b4": ["B2_ACC_MINBLOCKS_G2=4"],
+    "g2_b5": ["B2_ACC_MINBLOCKS_G2=5"],
+    "g2_b6": ["B2_ACC_MINBLOCKS_G2=6"],
     "m0_inl_b3": ["B2_MUL_VARIANT=0", "B2_MUL_NOINLINE=0", "B2_ACC_MINBLOCKS=3"],
     "m0_inl_b4": ["B2_MUL_VARIANT=0", "B2_MUL_NOINLINE=0", "B2_ACC_MINBLOCKS=4"],
     "m0_inl_b5": ["B2_MUL_VARIANT=0", "B2_MUL_NOINLINE=0", "B2_ACC_MINBLOCKS=5"],
