@@ -52,6 +52,21 @@ int b200zk_ctx_create(int device, b200zk_ctx** out) {
             return B200ZK_ERR_CUDA;
         }
     }
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        // lane 0 (the G2 MSM, issued first and by far the longest) sorts at the highest priority so that its bucket kernel
+        // starts filling the SMs after ~0.4 ms; the h pipeline comes next, the other lanes' sort phases are not urgent
+        // (their bucket kernels queue behind lane 0's anyway)
+        const int p_h = hi < lo ? hi + 1 : hi, p_mid = (lo + hi) / 2;
+        bool ok = cudaStreamCreateWithPriority(&ctx->hi_stream, cudaStreamNonBlocking, p_h) == cudaSuccess;
+        for (int k = 0; ok && k < 5; ++k) {
+            ok = cudaStreamCreateWithPriority(&ctx->lane_main[k], cudaStreamNonBlocking, k == 0 ? hi : p_mid) == cudaSuccess &&
+                 cudaStreamCreateWithPriority(&ctx->lane_acc[k], cudaStreamNonBlocking, lo) == cudaSuccess;
+            for (int j = 0; ok && j < 3; ++j) ok = cudaEventCreateWithFlags(&ctx->lane_ev[k][j], cudaEventDisableTiming) == cudaSuccess;
+        }
+        if (!ok) { b200zk_ctx_destroy(ctx); return B200ZK_ERR_CUDA; }
+    }
     *out = ctx;
     return B200ZK_OK;
 }
@@ -73,6 +88,12 @@ void b200zk_ctx_destroy(b200zk_ctx* ctx) {
         if (s.copy_done) cudaEventDestroy(s.copy_done);
         if (s.aux_done) cudaEventDestroy(s.aux_done);
         for (int k = 0; k < 4; ++k) if (s.stage_ev[k]) cudaEventDestroy(s.stage_ev[k]);
+    }
+    if (ctx->hi_stream) cudaStreamDestroy(ctx->hi_stream);
+    for (int k = 0; k < 5; ++k) {
+        if (ctx->lane_main[k]) cudaStreamDestroy(ctx->lane_main[k]);
+        if (ctx->lane_acc[k]) cudaStreamDestroy(ctx->lane_acc[k]);
+        for (int j = 0; j < 3; ++j) if (ctx->lane_ev[k][j]) cudaEventDestroy(ctx->lane_ev[k][j]);
     }
     for (auto& e : ctx->prof_pending) { cudaEventDestroy(e.start); cudaEventDestroy(e.stop); }
     delete ctx;
@@ -104,6 +125,7 @@ int b200zk_profile_enable(b200zk_ctx* ctx, int on) {
 
 static void prof_drain(b200zk_ctx* ctx) {
     std::lock_guard<std::mutex> g(ctx->prof_mu);
+    static const bool timeline = getenv("B200ZK_PROFILE_TIMELINE") && getenv("B200ZK_PROFILE_TIMELINE")[0] == '1';
     for (auto& e : ctx->prof_pending) {
         cudaEventSynchronize(e.stop);
         float ms = 0.f;
@@ -112,7 +134,15 @@ static void prof_drain(b200zk_ctx* ctx) {
             acc.first += 1;
             acc.second += ms;
         }
-        cudaEventDestroy(e.start);
+        bool keep = false;
+        if (timeline) {
+            if (!ctx->prof_base) { ctx->prof_base = e.start; keep = true; }
+            float t0 = 0.f, t1 = 0.f;
+            cudaEventElapsedTime(&t0, ctx->prof_base, e.start);
+            cudaEventElapsedTime(&t1, ctx->prof_base, e.stop);
+            ctx->prof_timeline.emplace_back(e.name, t0, t1);
+        }
+        if (!keep) cudaEventDestroy(e.start);
         cudaEventDestroy(e.stop);
     }
     ctx->prof_pending.clear();
@@ -123,6 +153,8 @@ int b200zk_profile_reset(b200zk_ctx* ctx) {
     prof_drain(ctx);
     std::lock_guard<std::mutex> g(ctx->prof_mu);
     ctx->prof_acc.clear();
+    ctx->prof_timeline.clear();
+    if (ctx->prof_base) { cudaEventDestroy(ctx->prof_base); ctx->prof_base = nullptr; }
     ctx->launches = 0;
     return B200ZK_OK;
 }
@@ -139,6 +171,14 @@ int b200zk_profile_json(b200zk_ctx* ctx, char* buf, size_t buf_len) {
             if (!first) os << ", ";
             first = false;
             os << "\"" << kv.first << "\": {\"launches\": " << kv.second.first << ", \"ms\": " << kv.second.second << "}";
+        }
+        if (!ctx->prof_timeline.empty()) {
+            os << (first ? "" : ", ") << "\"_timeline\": [";
+            for (size_t i = 0; i < ctx->prof_timeline.size(); ++i) {
+                auto& t = ctx->prof_timeline[i];
+                os << (i ? ", " : "") << "[\"" << std::get<0>(t) << "\", " << std::get<1>(t) << ", " << std::get<2>(t) << "]";
+            }
+            os << "]";
         }
     }
     os << "}";

@@ -9,6 +9,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/b200zk.h"
@@ -62,6 +63,14 @@ struct b200zk_ctx {
     size_t l2_persist_max = 0;      // cudaLimitPersistingL2CacheSize granted at creation
     size_t l2_window_max = 0;       // accessPolicyMaxWindowSize
     b200zk::Slot slots[3];
+    // prove_dev's streams.  hi_stream (highest priority): the h pipeline; lane_main[k] (middle priority): digit / sort /
+    // reduction kernels of MSM k; lane_acc[k] (lowest = default priority): its bucket kernel.  The block dispatcher
+    // serves the highest-priority pending kernel first, so the short kernels slip between the bucket kernels' blocks.
+    cudaStream_t hi_stream = nullptr;
+    cudaStream_t lane_main[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t lane_acc[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t lane_ev[5][3] = {};
+    unsigned msm_seg_hint = 0;      // set by prove_dev around its MSM launches (it holds every slot lock): reduction segment length
     std::string last_error;
     std::mutex err_mu;
     // profiling
@@ -69,6 +78,9 @@ struct b200zk_ctx {
     std::mutex prof_mu;
     std::vector<b200zk::ProfEntry> prof_pending;
     std::map<std::string, std::pair<uint64_t, double>> prof_acc;   // name -> (launches, ms)
+    // B200ZK_PROFILE_TIMELINE=1: (name, start, end) in ms since the first profiled launch (scheduling diagnostics)
+    cudaEvent_t prof_base = nullptr;
+    std::vector<std::tuple<std::string, float, float>> prof_timeline;
     std::atomic<uint64_t> launches{0};     // kernels launched (slots may be driven from different host threads)
     // NTT plans keyed by (log_n << 1 | inverse)
     std::mutex plan_mu;
@@ -155,6 +167,13 @@ static inline unsigned ceil_log2(size_t n) {
     return l;
 }
 
+struct MsmLane {
+    cudaStream_t st;          // digits, sort, merge, reduction, combine
+    DevBuf* ws;
+    cudaStream_t acc_st;      // bucket accumulation
+    cudaEvent_t ev_sorted, ev_acc;
+};
+
 // ---- entry points implemented across translation units -------------------------------------
 // ntt.cu
 int ntt_dev(b200zk_ctx* ctx, Slot& sl, const Fr* d_in, Fr* d_out, unsigned log_n, bool inverse, bool coset,
@@ -170,17 +189,20 @@ int fourstep_cols_p2p_dev(b200zk_ctx* ctx, Slot& sl, const Fr* d_in, void* const
 int mul_sub_dev(b200zk_ctx* ctx, Slot& sl, const Fr* a, const Fr* b, const Fr* c, Fr* out, size_t n);
 void ntt_free_plans(b200zk_ctx* ctx);
 // msm.cu
+// aux != 0: run on the slot's second compute stream / workspace (aux_stream, ws_msm_aux)
 int msm_g1_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n, void* d_out_xyzz,
-               cudaEvent_t bases_ready = nullptr);
+               cudaEvent_t bases_ready = nullptr, int aux = 0);
 int msm_g2_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n, void* d_out_xyzz,
-               cudaEvent_t bases_ready = nullptr);
+               cudaEvent_t bases_ready = nullptr, int aux = 0);
 int msm_g1_two_halves_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n1, size_t n2,
                           cudaEvent_t ev[4], void* d_out2);
 unsigned msm_table_windows(unsigned c);
 unsigned msm_table_auto_window(size_t n);
 int msm_table_build_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_bases, size_t n, unsigned c, void* d_table);
 int msm_table_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_table, const void* d_scalars, size_t n, unsigned c,
-                  void* d_out_xyzz);
+                  void* d_out_xyzz, int aux = 0);
+int msm_lane_dev(b200zk_ctx* ctx, const MsmLane& lane, int g2, unsigned tab_c, const void* d_bases, const void* d_scalars,
+                 size_t n, void* d_out_xyzz);
 int g1_sum_dev(b200zk_ctx* ctx, Slot& sl, const void* d_xyzz, size_t count, void* d_out_affine);
 int g2_sum_dev(b200zk_ctx* ctx, Slot& sl, const void* d_xyzz, size_t count, void* d_out_affine);
 int xyzz_sum_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_in, size_t count, size_t stride, void* d_out);

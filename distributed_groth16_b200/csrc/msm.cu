@@ -271,9 +271,27 @@ __global__ void k_msm_task_order(const uint32_t* offsets, const uint32_t* task_o
 template <class F>
 __global__ void __launch_bounds__(128, sizeof(F) > 32 ? B2_ACC_MINBLOCKS_G2 : B2_ACC_MINBLOCKS) k_msm_accumulate(const affine_t<F>* bases, const uint32_t* entries, const uint32_t* offsets,
                                  const uint32_t* task_off, const uint32_t* task_bucket, const uint32_t* order,
-                                 uint32_t nbuckets, uint32_t task_len, xyzz_t<F>* buckets, xyzz_t<F>* task_sums) {
-    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= task_off[nbuckets]) return;
+                                 uint32_t nbuckets, uint32_t task_len, uint32_t wave, xyzz_t<F>* buckets, xyzz_t<F>* task_sums) {
+    // Block order over the length-sorted task list: the first `wave` blocks (one per resident slot) take an evenly
+    // strided sample of the list, i.e. every length from the longest to the shortest, the others follow in descending
+    // order.  In plain descending order each generation of resident blocks has equal lengths and ends at the same
+    // moment: every SM stays held for ~1 ms at a time, and the short kernels of concurrent streams (sort phases of the
+    // next MSM, NTT passes of the h pipeline) wait that long for a slot whatever their priority.  Staggered once, the
+    // slots free up continuously and the longest-first property is kept for all but the sampled blocks.
+    const uint32_t ntask = task_off[nbuckets];
+    const uint32_t nblk = (ntask + blockDim.x - 1) / blockDim.x;
+    if (blockIdx.x >= nblk) return;
+    uint32_t vb = blockIdx.x;
+    const uint32_t stride = nblk / wave;
+    if (stride > 1) {
+        if (vb < wave) vb *= stride;
+        else {
+            uint32_t j = vb - wave;
+            vb = j < wave * (stride - 1) ? (j / (stride - 1)) * stride + j % (stride - 1) + 1 : wave * stride + (j - wave * (stride - 1));
+        }
+    }
+    uint32_t tid = vb * blockDim.x + threadIdx.x;
+    if (tid >= ntask) return;
     uint32_t t = order[tid];
     uint32_t g = task_bucket[t];
     uint32_t t0 = task_off[g], nt = task_off[g + 1] - t0;
@@ -478,7 +496,7 @@ static int exclusive_scan(b200zk_ctx* ctx, cudaStream_t st, const uint32_t* in, 
 template <class F>
 static int msm_dev_impl(b200zk_ctx* ctx, cudaStream_t st, DevBuf& ws_buf, const void* d_bases, const void* d_scalars, size_t n,
                         void* d_out, const char* acc_name, cudaEvent_t bases_ready, cudaEvent_t scalars_ready = nullptr,
-                        unsigned tab_c = 0) {
+                        unsigned tab_c = 0, const MsmLane* lane = nullptr) {
     if (scalars_ready) B2_CUDA_OK(ctx, cudaStreamWaitEvent(st, scalars_ready, 0));
     xyzz_t<F>* out = reinterpret_cast<xyzz_t<F>*>(d_out);
     if (n == 0) {
@@ -501,6 +519,11 @@ static int msm_dev_impl(b200zk_ctx* ctx, cudaStream_t st, DevBuf& ws_buf, const 
     const uint32_t B = 1u << (c - 1);
     const uint32_t nb = WB * B;
     uint32_t seg_len = B < 16 ? B : 16;
+    {
+        static const int seg_env = getenv("B200ZK_MSM_SEG") ? atoi(getenv("B200ZK_MSM_SEG")) : 0;
+        if (seg_env >= 2 && (seg_env & (seg_env - 1)) == 0 && (uint32_t)seg_env <= B) seg_len = (uint32_t)seg_env;
+        else if (ctx->msm_seg_hint && ctx->msm_seg_hint <= B) seg_len = ctx->msm_seg_hint;
+    }
     const uint32_t nseg = B / seg_len;
     const uint32_t wsplit = (fold && nseg >= 16 * 256) ? 16 : 1;
     const size_t total = (size_t)W * n;
@@ -615,9 +638,24 @@ static int msm_dev_impl(b200zk_ctx* ctx, cudaStream_t st, DevBuf& ws_buf, const 
         cudaGetLastError();
     }
     {
-        LaunchScope ls(ctx, st, acc_name);
-        k_msm_accumulate<F><<<(unsigned)((max_tasks + 127) / 128), 128, 0, st>>>(
-            reinterpret_cast<const affine_t<F>*>(d_bases), entries, offsets, task_off, task_bucket, order, nb, task_len, buckets, task_sums);
+        // lane (prove_dev): the bucket kernel goes to a lower-priority stream than the rest of this MSM, so that the
+        // short digit / sort / reduction kernels of concurrent MSMs are dispatched between its blocks instead of
+        // queueing behind whole bucket kernels of other streams
+        cudaStream_t ast = lane ? lane->acc_st : st;
+        if (lane) {
+            B2_CUDA_OK(ctx, cudaEventRecord(lane->ev_sorted, st));
+            B2_CUDA_OK(ctx, cudaStreamWaitEvent(ast, lane->ev_sorted, 0));
+        }
+        {
+            LaunchScope ls(ctx, ast, acc_name);
+            k_msm_accumulate<F><<<(unsigned)((max_tasks + 127) / 128), 128, 0, ast>>>(
+                reinterpret_cast<const affine_t<F>*>(d_bases), entries, offsets, task_off, task_bucket, order, nb, task_len,
+                (uint32_t)ctx->sm_count * (sizeof(F) > 32 ? B2_ACC_MINBLOCKS_G2 : B2_ACC_MINBLOCKS), buckets, task_sums);
+        }
+        if (lane) {
+            B2_CUDA_OK(ctx, cudaEventRecord(lane->ev_acc, ast));
+            B2_CUDA_OK(ctx, cudaStreamWaitEvent(st, lane->ev_acc, 0));
+        }
     }
     B2_TRY(check_launch(ctx, "k_msm_accumulate"));
     if (l2_window) {
@@ -658,12 +696,14 @@ static int msm_dev_impl(b200zk_ctx* ctx, cudaStream_t st, DevBuf& ws_buf, const 
 }
 
 int msm_g1_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n, void* d_out,
-               cudaEvent_t bases_ready) {
-    return msm_dev_impl<Fq>(ctx, sl.stream, sl.ws_msm, d_bases, d_scalars, n, d_out, "msm_accumulate_g1", bases_ready);
+               cudaEvent_t bases_ready, int aux) {
+    return msm_dev_impl<Fq>(ctx, aux ? sl.aux_stream : sl.stream, aux ? sl.ws_msm_aux : sl.ws_msm, d_bases, d_scalars, n, d_out,
+                            "msm_accumulate_g1", bases_ready);
 }
 int msm_g2_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n, void* d_out,
-               cudaEvent_t bases_ready) {
-    return msm_dev_impl<Fq2>(ctx, sl.stream, sl.ws_msm, d_bases, d_scalars, n, d_out, "msm_accumulate_g2", bases_ready);
+               cudaEvent_t bases_ready, int aux) {
+    return msm_dev_impl<Fq2>(ctx, aux ? sl.aux_stream : sl.stream, aux ? sl.ws_msm_aux : sl.ws_msm, d_bases, d_scalars, n, d_out,
+                             "msm_accumulate_g2", bases_ready);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -723,10 +763,18 @@ int msm_table_build_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_bases, 
               : table_build_impl<Fq>(ctx, sl.stream, d_bases, n, c, d_table);
 }
 int msm_table_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_table, const void* d_scalars, size_t n, unsigned c,
-                  void* d_out) {
+                  void* d_out, int aux) {
     if (c < 2 || c > 24) return set_error(ctx, B200ZK_ERR_ARG, "table window must be in [2, 24]");
-    return g2 ? msm_dev_impl<Fq2>(ctx, sl.stream, sl.ws_msm, d_table, d_scalars, n, d_out, "msm_accumulate_g2", nullptr, nullptr, c)
-              : msm_dev_impl<Fq>(ctx, sl.stream, sl.ws_msm, d_table, d_scalars, n, d_out, "msm_accumulate_g1", nullptr, nullptr, c);
+    cudaStream_t st = aux ? sl.aux_stream : sl.stream;
+    DevBuf& ws = aux ? sl.ws_msm_aux : sl.ws_msm;
+    return g2 ? msm_dev_impl<Fq2>(ctx, st, ws, d_table, d_scalars, n, d_out, "msm_accumulate_g2", nullptr, nullptr, c)
+              : msm_dev_impl<Fq>(ctx, st, ws, d_table, d_scalars, n, d_out, "msm_accumulate_g1", nullptr, nullptr, c);
+}
+
+int msm_lane_dev(b200zk_ctx* ctx, const MsmLane& lane, int g2, unsigned tab_c, const void* d_bases, const void* d_scalars,
+                 size_t n, void* d_out) {
+    return g2 ? msm_dev_impl<Fq2>(ctx, lane.st, *lane.ws, d_bases, d_scalars, n, d_out, "msm_accumulate_g2", nullptr, nullptr, tab_c, &lane)
+              : msm_dev_impl<Fq>(ctx, lane.st, *lane.ws, d_bases, d_scalars, n, d_out, "msm_accumulate_g1", nullptr, nullptr, tab_c, &lane);
 }
 
 // Host-staged G1 MSM in two halves on two streams: the H2D copy of the second half and the latency-bound tail of the

@@ -64,26 +64,38 @@ struct FinalizeArgs {
     int add_zero_terms;                                      // 0: the MSMs already covered index 0 (z[0] = 1)
 };
 
-__global__ void k_prove_finalize(FinalizeArgs f) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// Three warps, one active lane each: warp 0 -> A, warp 1 -> B (G2), warp 2 -> C (recomputes the A it needs for s * A).
+// The three normalisations (one field inversion each) were 0.28 ms back to back at the very end of the proof.
+__global__ void __launch_bounds__(96) k_prove_finalize(FinalizeArgs f) {
+    if ((threadIdx.x & 31) != 0 || blockIdx.x != 0) return;
+    const int role = threadIdx.x >> 5;
     const char* vk = reinterpret_cast<const char*>(f.vk);
-    affine_t<Fq> alpha = ldp<affine_t<Fq>>(vk), beta1 = ldp<affine_t<Fq>>(vk + 64), delta1 = ldp<affine_t<Fq>>(vk + 128);
-    affine_t<Fq2> beta2 = ldp<affine_t<Fq2>>(vk + 192), delta2 = ldp<affine_t<Fq2>>(vk + 320);
     Fr r = Fr::from_mont(f.rs[0]), s = Fr::from_mont(f.rs[1]);
-    Fr rs = Fr::from_mont(Fr::mul(f.rs[0], f.rs[1]));
     bool r_zero = r.is_zero(), s_zero = s.is_zero();
 
+    if (role == 1) {
+        affine_t<Fq2> beta2 = ldp<affine_t<Fq2>>(vk + 192), delta2 = ldp<affine_t<Fq2>>(vk + 320);
+        xyzz_t<Fq2> Bp = ldp<xyzz_t<Fq2>>(f.msm_b2);
+        if (f.add_zero_terms) xyzz_t<Fq2>::madd(Bp, ldp<affine_t<Fq2>>(f.b2_0), false);
+        xyzz_t<Fq2>::madd(Bp, beta2, false);
+        if (!s_zero) Bp = xyzz_t<Fq2>::add(Bp, xyzz_t<Fq2>::mul_scalar(xyzz_t<Fq2>::from_affine(delta2), s.l));
+        compress_g2(Bp, f.out + 32);
+        return;
+    }
+    affine_t<Fq> alpha = ldp<affine_t<Fq>>(vk), beta1 = ldp<affine_t<Fq>>(vk + 64), delta1 = ldp<affine_t<Fq>>(vk + 128);
     xyzz_t<Fq> d1 = xyzz_t<Fq>::from_affine(delta1);
-    xyzz_t<Fq> A = ldp<xyzz_t<Fq>>(f.msm_a);
-    if (f.add_zero_terms) xyzz_t<Fq>::madd(A, ldp<affine_t<Fq>>(f.a0), false);
-    xyzz_t<Fq>::madd(A, alpha, false);
-    if (!r_zero) A = xyzz_t<Fq>::add(A, xyzz_t<Fq>::mul_scalar(d1, r.l));
-
-    xyzz_t<Fq2> Bp = ldp<xyzz_t<Fq2>>(f.msm_b2);
-    if (f.add_zero_terms) xyzz_t<Fq2>::madd(Bp, ldp<affine_t<Fq2>>(f.b2_0), false);
-    xyzz_t<Fq2>::madd(Bp, beta2, false);
-    if (!s_zero) Bp = xyzz_t<Fq2>::add(Bp, xyzz_t<Fq2>::mul_scalar(xyzz_t<Fq2>::from_affine(delta2), s.l));
-
+    xyzz_t<Fq> A = xyzz_t<Fq>::identity();
+    if (role == 0 || !s_zero) {
+        A = ldp<xyzz_t<Fq>>(f.msm_a);
+        if (f.add_zero_terms) xyzz_t<Fq>::madd(A, ldp<affine_t<Fq>>(f.a0), false);
+        xyzz_t<Fq>::madd(A, alpha, false);
+        if (!r_zero) A = xyzz_t<Fq>::add(A, xyzz_t<Fq>::mul_scalar(d1, r.l));
+    }
+    if (role == 0) {
+        compress_g1(A, f.out);
+        return;
+    }
+    Fr rs = Fr::from_mont(Fr::mul(f.rs[0], f.rs[1]));
     xyzz_t<Fq> C = xyzz_t<Fq>::add(ldp<xyzz_t<Fq>>(f.msm_l), ldp<xyzz_t<Fq>>(f.msm_h));
     if (!s_zero) C = xyzz_t<Fq>::add(C, xyzz_t<Fq>::mul_scalar(A, s.l));
     if (!r_zero) {
@@ -94,8 +106,6 @@ __global__ void k_prove_finalize(FinalizeArgs f) {
         C = xyzz_t<Fq>::add(C, xyzz_t<Fq>::mul_scalar(B1, r.l));
         C = xyzz_t<Fq>::add(C, xyzz_t<Fq>::neg(xyzz_t<Fq>::mul_scalar(d1, rs.l)));
     }
-    compress_g1(A, f.out);
-    compress_g2(Bp, f.out + 32);
     compress_g1(C, f.out + 96);
 }
 
@@ -188,21 +198,91 @@ int prove_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, const Fr* d_a
     const char* aq = reinterpret_cast<const char*>(pk->a_query);
     const char* b1q = reinterpret_cast<const char*>(pk->b_g1_query);
     const char* b2q = reinterpret_cast<const char*>(pk->b_g2_query);
-    // query k of the key: its fixed-base table when pk_precompute_dev built one, else the generic MSM on the query
-    auto msm = [&](Slot& sl, int k, int g2, const void* query, const Fr* scalars, size_t n, void* out) -> int {
-        if (pk->tab_c[k]) return msm_table_dev(ctx, sl, g2, pk->tab[k], scalars, n, pk->tab_c[k], out);
-        return g2 ? msm_g2_dev(ctx, sl, query, scalars, n, out) : msm_g1_dev(ctx, sl, query, scalars, n, out);
-    };
-    int rc = msm(s1, 2, 1, b2q + 128, d_z + 1, n1, sm + o_b2);
-    if (!rc) rc = msm(s2, 0, 0, aq + 64, d_z + 1, n1, sm + o_a);
-    if (!rc) rc = msm(s2, 3, 0, pk->l_query, d_z + pk->n_inputs, n_aux, sm + o_l);
-    if (!rc && need_b1) rc = msm(s2, 1, 0, b1q + 64, d_z + 1, n1, sm + o_b1);
-    if (!rc) rc = h_circom_dev(ctx, s0, d_a, d_b, d_c, log_m, d_h);
-    if (!rc) rc = msm(s0, 4, 0, pk->h_query, d_h, m, sm + o_h);
-    cudaEventRecord(ev1, s1.stream);
-    cudaEventRecord(ev2, s2.stream);
-    cudaStreamWaitEvent(st, ev1, 0);
-    cudaStreamWaitEvent(st, ev2, 0);
+    // Five lanes, one per MSM (common.cuh: lane_main / lane_acc); query k runs over its fixed-base table when
+    // pk_precompute_dev built one, else as the generic MSM on the query.  Issue order: the h pipeline first (its
+    // NTT passes fill the SMs while the MSMs are still sorting), then the G2 MSM -- the longest bucket kernel and the
+    // longest latency-bound tail, which then overlaps the G1 bucket kernels -- then A, L, (B1), and H once h exists.
+    // With the MSMs on three default-priority streams the dispatcher drained whole bucket kernels before it looked
+    // at the next stream: one NTT pass waited 9 ms at 2^20 and the SMs idled ~2.5 ms mid-proof
+    // (profiles/r1c_prove_timeline.md).  B200ZK_PROVE_SCHED=slots keeps that older schedule for comparison.
+    static const char* sched_env = getenv("B200ZK_PROVE_SCHED");
+    static const bool use_lanes = sched_env && !strcmp(sched_env, "lanes");
+    static const bool use_hybrid = sched_env && !strcmp(sched_env, "hybrid");
+    int rc = B200ZK_OK;
+    ctx->msm_seg_hint = 32;            // bucket reduction in 32-bucket segments: 21% fewer group operations than 16, and
+                                       // its longer dependency chains are hidden by the concurrent MSMs (-0.3 ms at 2^20)
+    if (use_hybrid) {
+        // slots schedule, but the h pipeline on the high-priority stream and the H MSM on a lane
+        auto msm = [&](Slot& sl, int k, int g2, const void* query, const Fr* scalars, size_t n, void* out) -> int {
+            if (pk->tab_c[k]) return msm_table_dev(ctx, sl, g2, pk->tab[k], scalars, n, pk->tab_c[k], out);
+            return g2 ? msm_g2_dev(ctx, sl, query, scalars, n, out) : msm_g1_dev(ctx, sl, query, scalars, n, out);
+        };
+        cudaStreamWaitEvent(ctx->hi_stream, ev_in, 0);
+        cudaStream_t normal = s0.stream;
+        s0.stream = ctx->hi_stream;
+        rc = h_circom_dev(ctx, s0, d_a, d_b, d_c, log_m, d_h);
+        s0.stream = normal;
+        cudaEventRecord(ctx->lane_ev[4][2], ctx->hi_stream);
+        cudaStreamWaitEvent(ctx->lane_main[4], ctx->lane_ev[4][2], 0);
+        if (!rc) rc = msm(s1, 2, 1, b2q + 128, d_z + 1, n1, sm + o_b2);
+        if (!rc) rc = msm(s2, 0, 0, aq + 64, d_z + 1, n1, sm + o_a);
+        if (!rc) {
+            MsmLane lane{ctx->lane_main[4], &s0.ws_msm, ctx->lane_acc[4], ctx->lane_ev[4][0], ctx->lane_ev[4][1]};
+            rc = msm_lane_dev(ctx, lane, 0, pk->tab_c[4], pk->tab_c[4] ? pk->tab[4] : pk->h_query, d_h, m, sm + o_h);
+        }
+        if (!rc) rc = msm(s2, 3, 0, pk->l_query, d_z + pk->n_inputs, n_aux, sm + o_l);
+        if (!rc && need_b1) rc = msm(s2, 1, 0, b1q + 64, d_z + 1, n1, sm + o_b1);
+        cudaEventRecord(ev1, s1.stream);
+        cudaEventRecord(ev2, s2.stream);
+        cudaStreamWaitEvent(st, ev1, 0);
+        cudaStreamWaitEvent(st, ev2, 0);
+        cudaEventRecord(ctx->lane_ev[4][2], ctx->lane_main[4]);
+        cudaStreamWaitEvent(st, ctx->lane_ev[4][2], 0);
+    } else if (use_lanes) {
+        auto msm = [&](int lane_id, DevBuf& ws, int k, int g2, const void* query, const Fr* scalars, size_t n, void* out) -> int {
+            MsmLane lane{ctx->lane_main[lane_id], &ws, ctx->lane_acc[lane_id], ctx->lane_ev[lane_id][0], ctx->lane_ev[lane_id][1]};
+            return msm_lane_dev(ctx, lane, g2, pk->tab_c[k], pk->tab_c[k] ? pk->tab[k] : query, scalars, n, out);
+        };
+        cudaStreamWaitEvent(ctx->hi_stream, ev_in, 0);
+        cudaStream_t normal = s0.stream;
+        s0.stream = ctx->hi_stream;                          // h_circom_dev launches on the slot's stream
+        rc = h_circom_dev(ctx, s0, d_a, d_b, d_c, log_m, d_h);
+        s0.stream = normal;
+        cudaEventRecord(ctx->lane_ev[4][2], ctx->hi_stream);
+        cudaStreamWaitEvent(ctx->lane_main[4], ctx->lane_ev[4][2], 0);
+        // the lanes borrow the MSM workspaces of slots 1 and 2: order them after whatever those slots still have in flight
+        cudaEventRecord(ev1, s1.stream);
+        cudaEventRecord(ev2, s2.stream);
+        for (int k = 0; k < 4; ++k) {
+            cudaStreamWaitEvent(ctx->lane_main[k], ev_in, 0);
+            cudaStreamWaitEvent(ctx->lane_main[k], (k == 0 || k == 3) ? ev1 : ev2, 0);
+        }
+        if (!rc) rc = msm(0, s1.ws_msm, 2, 1, b2q + 128, d_z + 1, n1, sm + o_b2);
+        if (!rc) rc = msm(1, s2.ws_msm, 0, 0, aq + 64, d_z + 1, n1, sm + o_a);
+        if (!rc) rc = msm(2, s2.ws_msm_aux, 3, 0, pk->l_query, d_z + pk->n_inputs, n_aux, sm + o_l);
+        if (!rc && need_b1) rc = msm(3, s1.ws_msm_aux, 1, 0, b1q + 64, d_z + 1, n1, sm + o_b1);
+        if (!rc) rc = msm(4, s0.ws_msm, 4, 0, pk->h_query, d_h, m, sm + o_h);
+        for (int k = 0; k < 5; ++k) {
+            cudaEventRecord(ctx->lane_ev[k][2], ctx->lane_main[k]);
+            cudaStreamWaitEvent(st, ctx->lane_ev[k][2], 0);
+        }
+    } else {
+        auto msm = [&](Slot& sl, int k, int g2, const void* query, const Fr* scalars, size_t n, void* out) -> int {
+            if (pk->tab_c[k]) return msm_table_dev(ctx, sl, g2, pk->tab[k], scalars, n, pk->tab_c[k], out);
+            return g2 ? msm_g2_dev(ctx, sl, query, scalars, n, out) : msm_g1_dev(ctx, sl, query, scalars, n, out);
+        };
+        rc = msm(s1, 2, 1, b2q + 128, d_z + 1, n1, sm + o_b2);
+        if (!rc) rc = msm(s2, 0, 0, aq + 64, d_z + 1, n1, sm + o_a);
+        if (!rc) rc = msm(s2, 3, 0, pk->l_query, d_z + pk->n_inputs, n_aux, sm + o_l);
+        if (!rc && need_b1) rc = msm(s2, 1, 0, b1q + 64, d_z + 1, n1, sm + o_b1);
+        if (!rc) rc = h_circom_dev(ctx, s0, d_a, d_b, d_c, log_m, d_h);
+        if (!rc) rc = msm(s0, 4, 0, pk->h_query, d_h, m, sm + o_h);
+        cudaEventRecord(ev1, s1.stream);
+        cudaEventRecord(ev2, s2.stream);
+        cudaStreamWaitEvent(st, ev1, 0);
+        cudaStreamWaitEvent(st, ev2, 0);
+    }
+    ctx->msm_seg_hint = 0;
     if (rc) {
         cudaStreamSynchronize(st);
         cudaEventDestroy(ev_in); cudaEventDestroy(ev1); cudaEventDestroy(ev2);
@@ -219,7 +299,7 @@ int prove_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, const Fr* d_a
     f.add_zero_terms = 1;
     {
         LaunchScope ls(ctx, st, "prove_finalize");
-        k_prove_finalize<<<1, 32, 0, st>>>(f);
+        k_prove_finalize<<<1, 96, 0, st>>>(f);
     }
     rc = check_launch(ctx, "k_prove_finalize");
     cudaError_t e1 = cudaMemcpyAsync(proof_out, sm + o_out, 128, cudaMemcpyDeviceToHost, st);
@@ -254,7 +334,7 @@ int assemble_dev(b200zk_ctx* ctx, Slot& sl, const b200zk_pk* pk, const void* msm
     f.add_zero_terms = include_zero_terms;
     {
         LaunchScope ls(ctx, st, "prove_finalize");
-        k_prove_finalize<<<1, 32, 0, st>>>(f);
+        k_prove_finalize<<<1, 96, 0, st>>>(f);
     }
     B2_TRY(check_launch(ctx, "k_prove_finalize"));
     B2_CUDA_OK(ctx, cudaMemcpyAsync(proof_out, sm + 832, 128, cudaMemcpyDeviceToHost, st));
