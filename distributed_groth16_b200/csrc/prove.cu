@@ -124,7 +124,7 @@ void pk_free_tables(b200zk_pk* pk) {
 
 // Window tables for the five query vectors (msm.cu section 7).  c = 0: msm_table_auto_window(n) per query
 // (B200ZK_PK_TABLE_WINDOW overrides).  Skipped as a whole -- the generic MSM keeps running on the queries -- when
-// the tables would exceed B200ZK_PK_TABLE_MAX_GB (default 48) or the allocation fails.
+// the tables would exceed B200ZK_PK_TABLE_MAX_GB (default: 60% of the free HBM) or the allocation fails.
 int pk_precompute_dev(b200zk_ctx* ctx, b200zk_pk* pk, unsigned c_req) {
     pk_free_tables(pk);
     Slot& sl = ctx->slots[0];
@@ -134,7 +134,10 @@ int pk_precompute_dev(b200zk_ctx* ctx, b200zk_pk* pk, unsigned c_req) {
     const size_t cnt[5] = {n1, n1, n1, n_aux, pk->m};
     const size_t psz[5] = {64, 64, 128, 64, 64};
     if (const char* env = getenv("B200ZK_PK_TABLE_WINDOW")) { int v = atoi(env); if (v >= 2 && v <= 24) c_req = (unsigned)v; }
+    // budget: B200ZK_PK_TABLE_MAX_GB, else 60% of the HBM that is free right now (2^24 constraints: 84 GB of tables)
     double max_gb = 48.0;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) max_gb = 0.6 * (double)free_b / 1073741824.0;
     if (const char* env = getenv("B200ZK_PK_TABLE_MAX_GB")) max_gb = atof(env);
     unsigned cs[5];
     size_t total = 0;

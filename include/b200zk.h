@@ -161,7 +161,7 @@ int b200zk_pk_upload_dev(b200zk_ctx* ctx, const void* d_a_query, const void* d_b
 void b200zk_pk_free(b200zk_ctx* ctx, b200zk_pk* pk);
 /* (Re)build the key's fixed-base window tables (b200zk_msm_table_*): c = 0 picks b200zk_msm_table_auto_window(n)
  * per query, c = 0xFFFFFFFF drops the tables.  b200zk_pk_upload{,_dev} call this with c = 0 unless the environment
- * has B200ZK_PK_TABLES=0; tables that would exceed B200ZK_PK_TABLE_MAX_GB (default 48) are skipped and proving runs
+ * has B200ZK_PK_TABLES=0; tables that would exceed B200ZK_PK_TABLE_MAX_GB (default: 60% of the free HBM) are skipped and proving runs
  * the generic MSM on the queries.  The proof bytes do not depend on the choice.  b200zk_pk_table_bytes: HBM held by
  * the tables (0 = none). */
 int b200zk_pk_precompute(b200zk_ctx* ctx, b200zk_pk* pk, unsigned c);

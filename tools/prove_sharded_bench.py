@@ -55,7 +55,9 @@ def main():
     la, lb, lc = (cols_layout(v, cols, world, rank) for v in (a, b, c))
     rows = 1 << log_rows
     xch = par.P2PExchange(net, rows * rows // world)
-    out = {"config": "Groth16 prove 2^%d synthetic, sharded x%d" % (log_m, world), "log_m": log_m, "world": world}
+    out = {"config": "Groth16 prove 2^%d synthetic, sharded x%d" % (log_m, world), "log_m": log_m, "world": world,
+           "fixed_base_table_gb_per_rank": sum(t.numel() * 8 for t, _ in spk.tables.values()) / 2**30,
+           "fixed_base_windows": {k: c for k, (_, c) in spk.tables.items()}}
     proofs = {}
     for mode, x in (("nccl_all_to_all", None), ("p2p_fused", xch)):
         times = []
@@ -101,6 +103,7 @@ def main():
             single = prove.create_proof_dev(pk, z, a, b, c)
             ts.append((time.perf_counter() - t0) * 1e3)
         out["ms_prove_single_gpu"] = sorted(ts)[1]
+        out["single_gpu_table_gb"] = pk.table_bytes / 2**30
         out["bit_exact_sharded_vs_single_gpu"] = bool(single == proof)
         out["proof_hex"] = proof.hex()
         print("SHARDED_PROVE " + json.dumps(out))
