@@ -81,6 +81,9 @@ SIGNATURES = {
     "b200zk_pk_precompute": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint]),
     "b200zk_pk_table_bytes": (ctypes.c_size_t, [c_vp]),
     "b200zk_groth16_prove": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp]),
+    "b200zk_points_compress_dev": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_size_t, c_vp]),
+    "b200zk_points_decompress_dev": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_size_t, ctypes.c_int, c_vp,
+                                                    ctypes.POINTER(ctypes.c_size_t)]),
     "b200zk_xyzz_sum_dev": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_size_t, ctypes.c_size_t, c_vp]),
     "b200zk_groth16_assemble_dev": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp]),
     "b200zk_fixed_base_mul_dev": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, ctypes.c_size_t, c_vp]),

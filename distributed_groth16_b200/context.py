@@ -222,6 +222,35 @@ class Net:
                                                   c_vp(scalars.data_ptr()), n, int(c), c_vp(out_xyzz.data_ptr())))
         return out_xyzz
 
+    # -- ark-serialize Compress::Yes point codec (csrc/codec.cu) -------------------------------------
+    def points_compress(self, points, g2: bool = False, sid: int = 0):
+        """points: CUDA int64 tensor (n, 8 | 16) or host u64 array -> CUDA uint8 tensor (n, 32 | 64)."""
+        import torch
+        if not isinstance(points, torch.Tensor):
+            points = torch.from_numpy(_as_u64(points, 16 if g2 else 8).view(np.int64)).to(self._dev())
+        n = int(points.shape[0])
+        out = torch.empty((n, 64 if g2 else 32), dtype=torch.uint8, device=points.device)
+        self.check(self._lib.b200zk_points_compress_dev(self._h, int(sid), 1 if g2 else 0, c_vp(points.data_ptr()), n,
+                                                        c_vp(out.data_ptr())))
+        return out
+
+    def points_decompress(self, data, g2: bool = False, check_subgroup: bool = False, sid: int = 0):
+        """data: bytes / uint8 array / CUDA uint8 tensor of n encodings -> CUDA int64 tensor (n, 8 | 16) of affine points.
+        Raises B200zkError when an encoding is not a curve point (arkworks: SerializationError::InvalidData)."""
+        import torch
+        w = 64 if g2 else 32
+        if not isinstance(data, torch.Tensor):
+            raw = np.frombuffer(bytes(data), dtype=np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) else np.ascontiguousarray(data, dtype=np.uint8)
+            data = torch.from_numpy(raw.reshape(-1).copy()).to(self._dev())
+        if data.numel() % w:
+            raise B200zkError(_native.ERR_ARG, "encoding length is not a multiple of %d" % w)
+        n = data.numel() // w
+        out = torch.empty((n, 16 if g2 else 8), dtype=torch.int64, device=data.device)
+        bad = ctypes.c_size_t(0)
+        self.check(self._lib.b200zk_points_decompress_dev(self._h, int(sid), 1 if g2 else 0, c_vp(data.data_ptr()), n,
+                                                          1 if check_subgroup else 0, c_vp(out.data_ptr()), ctypes.byref(bad)))
+        return out
+
     def sum_points_dev(self, xyzz, count: int, g2: bool = False, sid: int = 0):
         w = 16 if g2 else 8
         out = np.zeros(w, dtype=np.uint64)

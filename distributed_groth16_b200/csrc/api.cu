@@ -553,6 +553,20 @@ int b200zk_groth16_prove_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const void* d
     return prove_dev(ctx, pk, (const Fr*)d_z, (const Fr*)d_a, (const Fr*)d_b, (const Fr*)d_c, r, s, mirror_bg1, proof_out);
 }
 
+int b200zk_points_compress_dev(b200zk_ctx* ctx, int stream, int g2, const void* d_affine, size_t n, void* d_bytes) {
+    if (!ctx || !valid_slot(stream) || (n && (!d_affine || !d_bytes))) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[stream];
+    std::lock_guard<std::mutex> g(sl.mu);
+    return points_compress_dev(ctx, sl, g2, d_affine, n, d_bytes);
+}
+int b200zk_points_decompress_dev(b200zk_ctx* ctx, int stream, int g2, const void* d_bytes, size_t n, int check_subgroup,
+                                 void* d_affine, size_t* n_invalid) {
+    if (!ctx || !valid_slot(stream) || (n && (!d_affine || !d_bytes))) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[stream];
+    std::lock_guard<std::mutex> g(sl.mu);
+    return points_decompress_dev(ctx, sl, g2, d_bytes, n, check_subgroup, d_affine, n_invalid);
+}
+
 int b200zk_xyzz_sum_dev(b200zk_ctx* ctx, int stream, int g2, const void* d_in, size_t count, size_t stride, void* d_out) {
     if (!ctx || !valid_slot(stream) || !d_in || !d_out || count == 0) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[stream];

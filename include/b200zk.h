@@ -167,6 +167,17 @@ void b200zk_pk_free(b200zk_ctx* ctx, b200zk_pk* pk);
 int b200zk_pk_precompute(b200zk_ctx* ctx, b200zk_pk* pk, unsigned c);
 size_t b200zk_pk_table_bytes(const b200zk_pk* pk);
 
+/* ---- ark-serialize Compress::Yes point codec (common/src/utils/serializer.rs:20-49: every proving / verifying key and
+ * proof of the reference travels in this form; zk-cli/src/main.rs:130-136) --------------------------------------------
+ * G1: 32 bytes = x little-endian, top bits of the last byte 0x80 (y is the larger of y, -y) / 0x40 (infinity);
+ * G2: 64 bytes = x.c0 || x.c1, flags in the last byte.  Affine points: 8 / 16 Montgomery u64 limbs, infinity all-zero.
+ * decompress: one square root per point on the device; *n_invalid = encodings that are not curve points (then the call
+ * returns B200ZK_ERR_ARG and those slots hold infinity).  check_subgroup != 0 also multiplies every G2 point by r
+ * (G1 has cofactor 1), i.e. arkworks' Validate::Yes. */
+int b200zk_points_compress_dev(b200zk_ctx* ctx, int stream, int g2, const void* d_affine, size_t n, void* d_bytes);
+int b200zk_points_decompress_dev(b200zk_ctx* ctx, int stream, int g2, const void* d_bytes, size_t n, int check_subgroup,
+                                 void* d_affine, size_t* n_invalid);
+
 /* ---- prove::{A,B,C}::compute + assembly (groth16/src/prove.rs:21-136, examples/sha256.rs:208-212)
  * z: full assignment (n_vars x 4 limbs, z[0] = 1); a, b, c: QAP evaluation vectors (m x 4 limbs);
  * r, s: 4 limbs (Montgomery; the reference always passes zero).  mirror_bg1 != 0 also runs the
