@@ -116,6 +116,41 @@ def run_reference(args):
     }))
 
 
+def measure_ntt(net, hbm_peak, pipe_peak):
+    """BASELINE config 3: Fr radix-2 NTT, 2^22 elements resident in HBM (forward, natural order in and out)."""
+    import torch
+    log_n = int(os.environ.get("B200ZK_BENCH_NTT_LOG_N", "22"))
+    n = 1 << log_n
+    x = net.generate_fr(3, n)
+    y = torch.empty_like(x)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=x.device)
+    for _ in range(3):
+        net.ntt_dev(x, y)
+    evs = []
+    for _ in range(10):
+        flush.fill_(1)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        net.ntt_dev(x, y)
+        a1.record()
+        evs.append((a0, a1))
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
+    ms = sum(ts) / len(ts)
+    back = torch.empty_like(x)
+    net.ntt_dev(y, back, inverse=True)
+    passes = -(-log_n // 8)
+    products = n * (log_n / 2.0 + 2.0 * (passes - 1))
+    return {"metric": "Fr NTT 2^%d (BN254 scalar field)" % log_n, "ms": ms, "ms_min": ts[0], "gelem_s": n / ms / 1e6,
+            "roofline": {"bound": "hbm", "achieved": 64.0 * n / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": 64.0 * n / ms / 1e6 / hbm_peak, "algorithmic_bytes_per_element": 64,
+                         "pipe": {"achieved": products / ms / 1e6, "peak": pipe_peak, "unit": "G modular products/s",
+                                  "frac": products / ms / 1e6 / pipe_peak,
+                                  "how": "n x (log n / 2 butterflies + 2 twiddle products per element per pass boundary)"}},
+            "round_trip_exact": bool((back == x).all()),
+            "timing": "CUDA events per transform, L2 flushed between transforms, 10 runs after 3 warm-ups"}
+
+
 def measure_prove(net, args, with_cpu):
     """Secondary metric of BASELINE.json: Groth16 prove ms, BN254, 2^20 constraints (m = n_vars = 2^20, dummy CRS
     built like groth16/examples/local_groth_bench.rs:21-52; witness and QAP evaluations resident in HBM)."""
@@ -356,6 +391,15 @@ def main():
     acc_ms = acc["ms"] / max(acc["launches"], 1)
     achieved = ALG_BYTES_PER_PAIR * n / (acc_ms * 1e-3) / 1e9
     kernel_ms = {k: round(v["ms"] / 5.0, 4) for k, v in rep.items()}
+    # what actually bounds the kernel: the multiplier pipe.  A 256-bit Montgomery product = 128 32-bit wide multiply-adds
+    # with carry, which issue at 32 lanes/clk/SM (tools/microbench.cu, profiles/r1_microbench_pipes.txt).
+    sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
+    pipe_peak = 32.0 * torch.cuda.get_device_properties(dev).multi_processor_count * sm_mhz * 1e6 / 128.0 / 1e9          # G products/s
+    adds = n * 16.0 * (1.0 - 2.0 ** -16)                                      # 16 signed 16-bit digits per scalar (GLV: 2 x 8)
+    pipe_ach = adds * 10.0 / (acc_ms * 1e-3) / 1e9                            # XYZZ mixed addition = 8M + 2S
+    pipe = {"bound": "fmaheavy (32-bit multiply-add with carry)", "achieved": pipe_ach, "peak": pipe_peak,
+            "unit": "G modular products/s", "frac": pipe_ach / pipe_peak,
+            "how": "bucket additions (n x 16 digits) x 10 products / kernel time; peak = 32 lanes/clk/SM x SMs x SM clock / 128"}
     out = {
         "metric": METRIC, "value": world * n / ms_step / 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": warm, "ms_per_step": ms_step, "ms_per_step_median": ms_step_sorted[len(ms_step_sorted) // 2],
@@ -371,7 +415,8 @@ def main():
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "msm_accumulate_g1", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": acc_ms,
-                     "note": "256-bit modular integer arithmetic: IMAD-bound by construction, HBM fraction is small"},
+                     "note": "256-bit modular integer arithmetic: IMAD-bound by construction, HBM fraction is small",
+                     "pipe": pipe},
         "kernel_ms_per_step": kernel_ms,
         "pipelined": pipelined,
         "fixed_base": fixed_base,
@@ -394,6 +439,8 @@ def main():
         out["cpu_baseline"] = {"value": n / dt / 1e6, "unit": UNIT, "cores": ncores, "kind": "port",
                                "sample": "one full 2^%d-pair G1 MSM, all host threads (%.2f s)" % (LOG_N, dt),
                                "bit_exact_vs_gpu": bool(world == 1 and (exp == res[0]).all()) if world == 1 else None}
+    if world == 1:
+        out["ntt"] = measure_ntt(net, peak, pipe_peak)
     if world == 1 and not args.no_prove:
         out["prove"] = measure_prove(net, args, not args.no_cpu_baseline)
     print(json.dumps(out))

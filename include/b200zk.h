@@ -167,6 +167,16 @@ void b200zk_pk_free(b200zk_ctx* ctx, b200zk_pk* pk);
 int b200zk_pk_precompute(b200zk_ctx* ctx, b200zk_pk* pk, unsigned c);
 size_t b200zk_pk_table_bytes(const b200zk_pk* pk);
 
+/* ---- Groth16::verify_with_processed_vk (groth16/examples/sha256.rs:229-254, mpc-api/src/main.rs:187-247) ----------
+ * e(A, B) == e(alpha_g1, beta_g2) * e(gamma_abc_g1[0] + sum_i x_i gamma_abc_g1[i+1], gamma_g2) * e(C, delta_g2), evaluated as
+ * one product of four Miller loops and one final exponentiation on the device.  Host buffers: affine points as Montgomery
+ * u64 limbs (G1 8, G2 16; infinity all-zero), public inputs n_public x 4 Montgomery limbs.  *is_valid = 1 / 0.  Points
+ * are taken as given (decompress with b200zk_points_decompress_dev(check_subgroup = 1) for arkworks' validation). */
+int b200zk_groth16_verify(b200zk_ctx* ctx, const uint64_t* alpha_g1, const uint64_t* beta_g2, const uint64_t* gamma_g2,
+                          const uint64_t* delta_g2, const uint64_t* gamma_abc_g1, size_t n_public,
+                          const uint64_t* public_inputs, const uint64_t* proof_a, const uint64_t* proof_b,
+                          const uint64_t* proof_c, int* is_valid);
+
 /* ---- ark-serialize Compress::Yes point codec (common/src/utils/serializer.rs:20-49: every proving / verifying key and
  * proof of the reference travels in this form; zk-cli/src/main.rs:130-136) --------------------------------------------
  * G1: 32 bytes = x little-endian, top bits of the last byte 0x80 (y is the larger of y, -y) / 0x40 (infinity);

@@ -244,4 +244,7 @@ def test_f3_gpu_setup_then_prove_sha256_and_verify_with_the_oracle_pairing(net):
         args = (g1(vk.alpha_g1), g2(vk.beta_g2), g2(vk.gamma_g2), g2(vk.delta_g2), ic)
         assert o.groth16_verify(*args, [pub], A, B, C), (r, s)
         assert not o.groth16_verify(*args, [pub + 1], A, B, C)
+        from distributed_groth16_b200.groth16 import verify                      # and by the GPU verifier (csrc/verify.cu)
+        assert verify.verify_proof(net, vk, layout.fr_to_arr([pub]), proof)
+        assert not verify.verify_proof(net, vk, layout.fr_to_arr([pub + 1]), proof)
     pk.free()
