@@ -109,10 +109,6 @@ __global__ void __launch_bounds__(96) k_prove_finalize(FinalizeArgs f) {
     compress_g1(C, f.out + 96);
 }
 
-// The five MSMs are spread over the three stream slots (the reference runs C's three d_msm on mux streams
-// 0/1/2 concurrently, prove.rs:119-125): slot 0 = h pipeline then MSM(h_query, h); slot 1 = the G2 MSM;
-// slot 2 = MSM(a_query) then MSM(l_query) (then MSM(b_g1_query)).  The latency-bound tails of one MSM
-// (bucket reduction, Horner) then overlap the throughput-bound bucket accumulation of another.
 void pk_free_tables(b200zk_pk* pk) {
     for (int k = 0; k < 5; ++k) {
         if (pk->tab[k]) cudaFree(pk->tab[k]);
@@ -201,47 +197,21 @@ int prove_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, const Fr* d_a
     const char* aq = reinterpret_cast<const char*>(pk->a_query);
     const char* b1q = reinterpret_cast<const char*>(pk->b_g1_query);
     const char* b2q = reinterpret_cast<const char*>(pk->b_g2_query);
-    // Five lanes, one per MSM (common.cuh: lane_main / lane_acc); query k runs over its fixed-base table when
-    // pk_precompute_dev built one, else as the generic MSM on the query.  Issue order: the h pipeline first (its
-    // NTT passes fill the SMs while the MSMs are still sorting), then the G2 MSM -- the longest bucket kernel and the
-    // longest latency-bound tail, which then overlaps the G1 bucket kernels -- then A, L, (B1), and H once h exists.
-    // With the MSMs on three default-priority streams the dispatcher drained whole bucket kernels before it looked
-    // at the next stream: one NTT pass waited 9 ms at 2^20 and the SMs idled ~2.5 ms mid-proof
-    // (profiles/r1c_prove_timeline.md).  B200ZK_PROVE_SCHED=slots keeps that older schedule for comparison.
+    // Query k runs over its fixed-base table when pk_precompute_dev built one, else as the generic MSM on the query.
+    // Default schedule ("slots"): the five MSMs are spread over the three stream slots, as the reference runs C's
+    // three d_msm on mux streams 0/1/2 (prove.rs:119-125): slot 1 = the G2 MSM (issued first: longest bucket kernel and
+    // longest latency-bound tail), slot 2 = MSM(a_query), MSM(l_query), (MSM(b_g1_query)), slot 0 = h pipeline then
+    // MSM(h_query, h).  The tails of one MSM then overlap the bucket kernels of another.
+    // B200ZK_PROVE_SCHED=lanes is the alternative that was measured and lost (19.0 vs 18.5 ms at 2^20): one stream pair
+    // per MSM (common.cuh: lane_main / lane_acc), bucket kernels at the lowest priority, h pipeline at the highest.
+    // It removes the idle stretches of the default schedule, but the proof is bound by total multiplier work and the
+    // reductions then compete with the bucket kernels (profiles/r1c_prove_timeline.md).
     static const char* sched_env = getenv("B200ZK_PROVE_SCHED");
     static const bool use_lanes = sched_env && !strcmp(sched_env, "lanes");
-    static const bool use_hybrid = sched_env && !strcmp(sched_env, "hybrid");
     int rc = B200ZK_OK;
     ctx->msm_seg_hint = 32;            // bucket reduction in 32-bucket segments: 21% fewer group operations than 16, and
                                        // its longer dependency chains are hidden by the concurrent MSMs (-0.3 ms at 2^20)
-    if (use_hybrid) {
-        // slots schedule, but the h pipeline on the high-priority stream and the H MSM on a lane
-        auto msm = [&](Slot& sl, int k, int g2, const void* query, const Fr* scalars, size_t n, void* out) -> int {
-            if (pk->tab_c[k]) return msm_table_dev(ctx, sl, g2, pk->tab[k], scalars, n, pk->tab_c[k], out);
-            return g2 ? msm_g2_dev(ctx, sl, query, scalars, n, out) : msm_g1_dev(ctx, sl, query, scalars, n, out);
-        };
-        cudaStreamWaitEvent(ctx->hi_stream, ev_in, 0);
-        cudaStream_t normal = s0.stream;
-        s0.stream = ctx->hi_stream;
-        rc = h_circom_dev(ctx, s0, d_a, d_b, d_c, log_m, d_h);
-        s0.stream = normal;
-        cudaEventRecord(ctx->lane_ev[4][2], ctx->hi_stream);
-        cudaStreamWaitEvent(ctx->lane_main[4], ctx->lane_ev[4][2], 0);
-        if (!rc) rc = msm(s1, 2, 1, b2q + 128, d_z + 1, n1, sm + o_b2);
-        if (!rc) rc = msm(s2, 0, 0, aq + 64, d_z + 1, n1, sm + o_a);
-        if (!rc) {
-            MsmLane lane{ctx->lane_main[4], &s0.ws_msm, ctx->lane_acc[4], ctx->lane_ev[4][0], ctx->lane_ev[4][1]};
-            rc = msm_lane_dev(ctx, lane, 0, pk->tab_c[4], pk->tab_c[4] ? pk->tab[4] : pk->h_query, d_h, m, sm + o_h);
-        }
-        if (!rc) rc = msm(s2, 3, 0, pk->l_query, d_z + pk->n_inputs, n_aux, sm + o_l);
-        if (!rc && need_b1) rc = msm(s2, 1, 0, b1q + 64, d_z + 1, n1, sm + o_b1);
-        cudaEventRecord(ev1, s1.stream);
-        cudaEventRecord(ev2, s2.stream);
-        cudaStreamWaitEvent(st, ev1, 0);
-        cudaStreamWaitEvent(st, ev2, 0);
-        cudaEventRecord(ctx->lane_ev[4][2], ctx->lane_main[4]);
-        cudaStreamWaitEvent(st, ctx->lane_ev[4][2], 0);
-    } else if (use_lanes) {
+    if (use_lanes) {
         auto msm = [&](int lane_id, DevBuf& ws, int k, int g2, const void* query, const Fr* scalars, size_t n, void* out) -> int {
             MsmLane lane{ctx->lane_main[lane_id], &ws, ctx->lane_acc[lane_id], ctx->lane_ev[lane_id][0], ctx->lane_ev[lane_id][1]};
             return msm_lane_dev(ctx, lane, g2, pk->tab_c[k], pk->tab_c[k] ? pk->tab[k] : query, scalars, n, out);
