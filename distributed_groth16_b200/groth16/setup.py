@@ -11,13 +11,12 @@ of tau) times the transposed constraint matrices (CSR mat-vec), query scalars by
 by fixed-base multiplication of the generators.  The host only reorders index arrays and builds small scalar vectors."""
 from __future__ import annotations
 
-import ctypes
 from dataclasses import dataclass
 
 import numpy as np
 
 from .._native import c_vp
-from ..formats import FR_MODULUS, coo_to_csr
+from ..formats import FR_MODULUS
 from .proving_key import ProvingKey
 from .qap import ConstraintMatrices
 

@@ -34,7 +34,7 @@ through naive-definition cross-checks.
 from __future__ import annotations
 
 import struct
-from typing import Iterable, List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 # --------------------------------------------------------------------------------------
 # Constants.  p, r are the BN254 base / scalar primes; both are re-derived from the BN

@@ -13,8 +13,6 @@ readSharedRWMemory(j).
 """
 from __future__ import annotations
 
-import struct
-
 M32, M64 = 0xFFFFFFFF, 0xFFFFFFFFFFFFFFFF
 
 

@@ -2,8 +2,6 @@
 where /root/reference does not exist.  The byte layout follows ark-circom/src/zkey.rs:53-387 (sections 1-9)."""
 import struct
 
-import numpy as np
-
 Q = 21888242871839275222246405745257275088696311157297823662689037894645226208583
 R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
 

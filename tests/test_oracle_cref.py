@@ -1,8 +1,6 @@
 """The C++ CPU twin (oracle/bn254_ref.cpp) against the Python big-int oracle (oracle/bn254.py)."""
 import random
 
-import numpy as np
-
 from oracle import bn254 as o, layout as L
 
 

@@ -3,7 +3,6 @@ import json
 import os
 
 import numpy as np
-import pytest
 
 from oracle import bn254 as o, layout
 
