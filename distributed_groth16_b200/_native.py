@@ -81,6 +81,8 @@ SIGNATURES = {
     "b200zk_pk_precompute": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint]),
     "b200zk_pk_table_bytes": (ctypes.c_size_t, [c_vp]),
     "b200zk_groth16_prove": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_int, c_vp]),
+    "b200zk_points_matmul_dev": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_size_t, ctypes.c_size_t, c_vp,
+                                                ctypes.c_size_t, c_vp]),
     "b200zk_groth16_verify": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t, c_vp, c_vp, c_vp, c_vp,
                                              ctypes.POINTER(ctypes.c_int)]),
     "b200zk_points_compress_dev": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_size_t, c_vp]),

@@ -208,6 +208,7 @@ class Net:
         table = torch.empty((w * n, 16 if g2 else 8), dtype=torch.int64, device=bases.device)
         self.check(self._lib.b200zk_msm_table_build_dev(self._h, int(sid), 1 if g2 else 0, c_vp(bases.data_ptr()), n, int(c),
                                                         c_vp(table.data_ptr())))
+        self.sync(sid)                 # one-off preprocessing: hand back a finished table whatever stream the caller uses
         return table
 
     def msm_table_dev(self, table, scalars, c: int, out_xyzz=None, g2: bool = False, sid: int = 0):
@@ -232,6 +233,7 @@ class Net:
         out = torch.empty((n, 64 if g2 else 32), dtype=torch.uint8, device=points.device)
         self.check(self._lib.b200zk_points_compress_dev(self._h, int(sid), 1 if g2 else 0, c_vp(points.data_ptr()), n,
                                                         c_vp(out.data_ptr())))
+        self.sync(sid)
         return out
 
     def points_decompress(self, data, g2: bool = False, check_subgroup: bool = False, sid: int = 0):

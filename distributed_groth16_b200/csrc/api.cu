@@ -567,6 +567,14 @@ int b200zk_points_decompress_dev(b200zk_ctx* ctx, int stream, int g2, const void
     return points_decompress_dev(ctx, sl, g2, d_bytes, n, check_subgroup, d_affine, n_invalid);
 }
 
+int b200zk_points_matmul_dev(b200zk_ctx* ctx, int stream, int g2, const void* d_points, size_t n_chunks, size_t l,
+                             const void* d_matrix, size_t rows, void* d_out) {
+    if (!ctx || !valid_slot(stream) || (n_chunks && rows && (!d_points || !d_matrix || !d_out))) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[stream];
+    std::lock_guard<std::mutex> g(sl.mu);
+    return points_matmul_dev(ctx, sl, g2, d_points, n_chunks, l, d_matrix, rows, d_out);
+}
+
 int b200zk_groth16_verify(b200zk_ctx* ctx, const uint64_t* alpha_g1, const uint64_t* beta_g2, const uint64_t* gamma_g2,
                           const uint64_t* delta_g2, const uint64_t* gamma_abc_g1, size_t n_public, const uint64_t* public_inputs,
                           const uint64_t* proof_a, const uint64_t* proof_b, const uint64_t* proof_c, int* is_valid) {

@@ -14,6 +14,17 @@ import numpy as np
 from ..context import MpcNetError, MultiplexedStreamID, Net
 
 
+def bitrev_indices(n: int) -> np.ndarray:
+    """rev[i] = i with its log2(n) bits reversed (int64)."""
+    lg = n.bit_length() - 1
+    assert 1 << lg == n
+    idx = np.arange(n, dtype=np.uint64)
+    rev = np.zeros(n, dtype=np.uint64)
+    for b in range(lg):
+        rev |= ((idx >> np.uint64(b)) & np.uint64(1)) << np.uint64(lg - 1 - b)
+    return rev.astype(np.int64)
+
+
 def fft_in_place_rearrange(data: np.ndarray) -> np.ndarray:
     """Bit-reversal permutation (dfft/mod.rs:258-271); host-side index shuffle, returns a copy."""
     data = np.ascontiguousarray(data, dtype=np.uint64).reshape(-1, 4)

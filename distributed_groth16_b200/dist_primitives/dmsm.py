@@ -121,6 +121,41 @@ def unpackexp(shares, degree2: bool, pp, net: Net, g2: bool = False) -> np.ndarr
     return e[: pp.l]
 
 
+def packexp_from_public_batch(points, pp, net: Net, g2: bool = False):
+    """packexp_from_public of every l-point chunk of `points` in one kernel launch (b200zk_points_matmul_dev with the
+    sharing's pack matrix): CUDA int64 (chunks * l, w) -> (chunks, n, w).  A trailing partial chunk is padded with the
+    identity, as `cfg_chunks!` + `packexp_from_public`'s resize do (proving_key.rs:66-80, dmsm/mod.rs:54)."""
+    import torch
+    from .._native import c_vp
+    w = 16 if g2 else 8
+    k = int(points.shape[0])
+    chunks = -(-k // pp.l)
+    if chunks * pp.l != k:
+        pad = torch.zeros((chunks * pp.l, w), dtype=torch.int64, device=points.device)
+        pad[:k] = points
+        points = pad
+    m = net.to_device(pp.pack_matrix().reshape(-1, 4))
+    out = torch.empty((chunks, pp.n, w), dtype=torch.int64, device=points.device)
+    net.check(net._lib.b200zk_points_matmul_dev(net._h, 0, 1 if g2 else 0, c_vp(points.data_ptr()), chunks, pp.l,
+                                                c_vp(m.data_ptr()), pp.n, c_vp(out.data_ptr())))
+    net.sync(0)
+    return out
+
+
+def unpackexp_batch(shares, degree2: bool, pp, net: Net, g2: bool = False):
+    """unpackexp of (chunks, n, w) share vectors in one launch -> (chunks, l, w)."""
+    import torch
+    from .._native import c_vp
+    w = 16 if g2 else 8
+    chunks = int(shares.shape[0])
+    m = net.to_device(pp.unpack_matrix(degree2).reshape(-1, 4))
+    out = torch.empty((chunks, pp.l, w), dtype=torch.int64, device=shares.device)
+    net.check(net._lib.b200zk_points_matmul_dev(net._h, 0, 1 if g2 else 0, c_vp(shares.data_ptr()), chunks, pp.n,
+                                                c_vp(m.data_ptr()), pp.l, c_vp(out.data_ptr())))
+    net.sync(0)
+    return out
+
+
 def d_msm_mpc(bases_shares, scalar_shares, pp, net: Net, g2: bool = False) -> GroupElement:
     """The reference protocol itself, all n parties simulated on this GPU (what LocalTestNet does in-process,
     mpc-net/src/multi.rs:289-316): every party runs `G::msm` on its packed shares (dmsm/mod.rs:82); the king unpacks the

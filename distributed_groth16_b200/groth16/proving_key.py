@@ -73,3 +73,27 @@ class ProvingKey:
             self.free()
         except Exception:
             pass
+
+
+class PackedProvingKeyShare:
+    """`PackedProvingKeyShare` (groth16/src/proving_key.rs:16-27): one party's packed shares of the five query vectors,
+    s = a_query[1..], u = h_query, w = l_query, h = b_g1_query[1..] (G1) and v = b_g2_query[1..] (G2); one share per
+    l-point chunk.  Arrays are CUDA int64 tensors (chunks, 8 | 16) of affine Montgomery limbs."""
+
+    def __init__(self, s, u, v, w, h):
+        self.s, self.u, self.v, self.w, self.h = s, u, v, w, h
+
+    @staticmethod
+    def pack_from_arkworks_proving_key(net: Net, a_query, b_g1_query, b_g2_query, l_query, h_query, pp) -> list:
+        """proving_key.rs:35-110: every chunk of every query goes through `packexp_from_public`; here one
+        `b200zk_points_matmul_dev` launch per query.  Returns pp.n PackedProvingKeyShare objects."""
+        from ..dist_primitives.dmsm import packexp_from_public_batch
+        dev = lambda a, w: a if hasattr(a, "data_ptr") else net.to_device(_as_u64(a, w))
+        packed = {
+            "s": packexp_from_public_batch(dev(a_query, 8)[1:].contiguous(), pp, net),
+            "u": packexp_from_public_batch(dev(h_query, 8), pp, net),
+            "w": packexp_from_public_batch(dev(l_query, 8), pp, net),
+            "h": packexp_from_public_batch(dev(b_g1_query, 8)[1:].contiguous(), pp, net),
+            "v": packexp_from_public_batch(dev(b_g2_query, 16)[1:].contiguous(), pp, net, g2=True),
+        }
+        return [PackedProvingKeyShare(**{k: t[:, p].contiguous() for k, t in packed.items()}) for p in range(pp.n)]

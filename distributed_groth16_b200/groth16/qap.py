@@ -66,6 +66,27 @@ class QAP:
     domain: Radix2Domain
 
 
+def qap_pss(q: QAP, pp) -> list:
+    """`QAP::pss` (groth16/src/qap.rs:143-187): bit-reverse a, b, c, cut each into m/l strided chunks
+    (x[i], x[i + m/l], ...), pack every chunk, and hand party p the p-th share of every chunk.
+    Returns pp.n PackedQAPShare objects whose vectors are CUDA int64 (m/l, 4) tensors."""
+    import torch
+    from ..dist_primitives.dfft import bitrev_indices
+    m = q.domain.size()
+    assert m % pp.l == 0
+    idx = torch.from_numpy(bitrev_indices(m)).to(q.a.device)
+
+    def pack(x):
+        xr = torch.empty_like(x)
+        xr[idx] = x                                                   # fft_in_place_rearrange
+        chunks = xr.reshape(pp.l, m // pp.l, 4).permute(1, 0, 2).contiguous()     # chunk i = x[i], x[i + m/l], ...
+        return pp.pack_from_public_batch(chunks)                      # (m/l, n, 4)
+
+    pa, pb, pc = pack(q.a), pack(q.b), pack(q.c)
+    return [PackedQAPShare(q.num_inputs, q.num_constraints, pa[:, p].contiguous(), pb[:, p].contiguous(), pc[:, p].contiguous(),
+                           q.domain, rearranged=True) for p in range(pp.n)]
+
+
 def qap(matrices: ConstraintMatrices, full_assignment, net=None) -> QAP:
     """full_assignment: CUDA int64 (n_vars, 4) tensor, Montgomery form."""
     import torch

@@ -44,3 +44,42 @@ class PackedSharingParams:
     def unpack2(self, shares) -> np.ndarray:
         c = self.net.ntt(_resize(shares, self.share_size), inverse=True)
         return self.net.ntt(_resize(c, self.secret2_size), coset=True)[: 2 * self.l: 2]
+
+    # whole vectors at once ------------------------------------------------------------------------
+    def pack_from_public_batch(self, secrets):
+        """secrets: CUDA int64 tensor (chunks, l, 4) -> shares (chunks, n, 4): pack_from_public of every chunk, as two
+        batched device transforms (what QAP::pss does chunk by chunk, groth16/src/qap.rs:151-166)."""
+        import torch
+        chunks = int(secrets.shape[0])
+        assert tuple(secrets.shape[1:]) == (self.l, 4)
+        x = torch.zeros((chunks, self.secret_size, 4), dtype=torch.int64, device=secrets.device)
+        x[:, : self.l] = secrets
+        coeffs = self.net.ntt_dev(x, inverse=True, coset=True, batch=chunks)
+        y = torch.zeros((chunks, self.share_size, 4), dtype=torch.int64, device=secrets.device)
+        y[:, : self.secret_size] = coeffs
+        return self.net.ntt_dev(y, batch=chunks)
+
+    def pack_matrix(self) -> np.ndarray:
+        """(n, l) matrix M with shares = M * secrets (pack is linear): column i = pack_from_public(e_i)."""
+        if getattr(self, "_pack_m", None) is None:
+            from .._constants import FR_ONE_MONT
+            cols = []
+            for i in range(self.l):
+                e = np.zeros((self.l, 4), dtype=np.uint64)
+                e[i] = np.array(FR_ONE_MONT, dtype=np.uint64)
+                cols.append(self.pack_from_public(e))
+            self._pack_m = np.ascontiguousarray(np.stack(cols, axis=1))        # (n, l, 4)
+        return self._pack_m
+
+    def unpack_matrix(self, degree2: bool = False) -> np.ndarray:
+        """(l, n) matrix U with secrets = U * shares: column j = unpack(e_j) (unpack2 when degree2)."""
+        key = "_unpack2_m" if degree2 else "_unpack_m"
+        if getattr(self, key, None) is None:
+            from .._constants import FR_ONE_MONT
+            cols = []
+            for j in range(self.n):
+                e = np.zeros((self.n, 4), dtype=np.uint64)
+                e[j] = np.array(FR_ONE_MONT, dtype=np.uint64)
+                cols.append(self.unpack2(e) if degree2 else self.unpack(e))
+            setattr(self, key, np.ascontiguousarray(np.stack(cols, axis=1)))     # (l, n, 4)
+        return getattr(self, key)

@@ -167,6 +167,13 @@ void b200zk_pk_free(b200zk_ctx* ctx, b200zk_pk* pk);
 int b200zk_pk_precompute(b200zk_ctx* ctx, b200zk_pk* pk, unsigned c);
 size_t b200zk_pk_table_bytes(const b200zk_pk* pk);
 
+/* ---- packexp_from_public / unpackexp over whole vectors (dist-primitives/src/dmsm/mod.rs:7-68, applied chunk by chunk to
+ * the proving key in groth16/src/proving_key.rs:35-110): out[k * rows + j] = sum_{i < l} matrix[j * l + i] * points[k * l + i]
+ * for every chunk k < n_chunks.  matrix: rows x l Fr elements (Montgomery) -- the pack (n x l) or unpack (l x n) matrix of
+ * the PackedSharingParams; points / out affine (G1 8, G2 16 u64 limbs). */
+int b200zk_points_matmul_dev(b200zk_ctx* ctx, int stream, int g2, const void* d_points, size_t n_chunks, size_t l,
+                             const void* d_matrix, size_t rows, void* d_out);
+
 /* ---- Groth16::verify_with_processed_vk (groth16/examples/sha256.rs:229-254, mpc-api/src/main.rs:187-247) ----------
  * e(A, B) == e(alpha_g1, beta_g2) * e(gamma_abc_g1[0] + sum_i x_i gamma_abc_g1[i+1], gamma_g2) * e(C, delta_g2), evaluated as
  * one product of four Miller loops and one final exponentiation on the device.  Host buffers: affine points as Montgomery

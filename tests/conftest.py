@@ -19,6 +19,7 @@ def net():
     the product has no CPU fallback, and a silent skip would hide 'native code not loaded'."""
     from distributed_groth16_b200 import Net
     n = Net(0)
+    n.use_torch_stream(0)          # slot 0 launches on torch's current stream: tensor ops and kernels stay ordered
     yield n
     n.close()
 
