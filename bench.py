@@ -104,7 +104,7 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     val = n / dt / 1e6
     sample = "full 2^%d-pair G1 MSM per step, %d OpenMP threads (windows in parallel, as arkworks+rayon)" % (LOG_N, cores)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32x8 Montgomery (256-bit modular integers)", "data": "synthetic",
@@ -113,7 +113,7 @@ def run_reference(args):
                            "cannot be built in this image"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def measure_ntt(net, hbm_peak, pipe_peak):
@@ -198,7 +198,30 @@ def measure_prove(net, args, with_cpu):
     return res
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL's `NCCL version ...` banner comes from C
+    code on fd 1): keep a private duplicate of fd 1 for the JSON line and point fd 1 at stderr for everything else."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -443,7 +466,7 @@ def main():
         out["ntt"] = measure_ntt(net, peak, pipe_peak)
     if world == 1 and not args.no_prove:
         out["prove"] = measure_prove(net, args, not args.no_cpu_baseline)
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
