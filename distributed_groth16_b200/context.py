@@ -229,6 +229,7 @@ class Net:
         import torch
         if not isinstance(points, torch.Tensor):
             points = torch.from_numpy(_as_u64(points, 16 if g2 else 8).view(np.int64)).to(self._dev())
+        points = points.contiguous()
         n = int(points.shape[0])
         out = torch.empty((n, 64 if g2 else 32), dtype=torch.uint8, device=points.device)
         self.check(self._lib.b200zk_points_compress_dev(self._h, int(sid), 1 if g2 else 0, c_vp(points.data_ptr()), n,
@@ -244,6 +245,7 @@ class Net:
         if not isinstance(data, torch.Tensor):
             raw = np.frombuffer(bytes(data), dtype=np.uint8) if isinstance(data, (bytes, bytearray, memoryview)) else np.ascontiguousarray(data, dtype=np.uint8)
             data = torch.from_numpy(raw.reshape(-1).copy()).to(self._dev())
+        data = data.contiguous()
         if data.numel() % w:
             raise B200zkError(_native.ERR_ARG, "encoding length is not a multiple of %d" % w)
         n = data.numel() // w
