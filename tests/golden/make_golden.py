@@ -68,6 +68,8 @@ def main():
     d = REF + "/fixtures/million/"
     g["snarkjs_million"] = dict(vk=json.load(open(d + "verification_key.json")), proof=json.load(open(d + "proof.json")),
                                 public=json.load(open(d + "public.json")))
+    # (ark-circom/test-vectors/{proof,public,verification_key}.json is a stale triple: it does not satisfy the
+    #  verification equation -- checked with the oracle pairing -- so it is not used as a fixture)
     r1 = open(REF + "/fixtures/sha256/sha256.r1cs", "rb").read()
     secs = o._sections(r1, b"r1cs")
     off, _ = secs[1][0]

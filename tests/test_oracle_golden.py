@@ -121,3 +121,23 @@ def test_f2_sha256_witness_fixture_satisfies_the_r1cs_and_the_reference_kat():
             v[int(r_)] = (v[int(r_)] + x * w[int(c_)]) % o.R
         acc[k] = v
     assert all(x * y % o.R == z for x, y, z in zip(acc["a"], acc["b"], acc["c"]))
+
+
+def test_pairing_value_matches_the_snarkjs_vk_alphabeta_12():
+    """Absolute known answer for the pairing itself: snarkjs stores e(alpha, beta) in the verification key
+    (fixtures/million/verification_key.json, `vk_alphabeta_12`, Fq12 as the 2 x 3 x 2 tower over w^2 = v, v^3 = 9 + u).
+    ffjavascript's final exponentiation uses the Fuentes-Castaneda hard part, which raises to m * (p^4 - p^2 + 1)/r with
+    m = 2u(6u^2 + 3u + 1), so the stored value is e(alpha, beta)^m for the plain (p^12 - 1)/r pairing of the oracle."""
+    vk = gold["snarkjs_million"]["vk"]
+    g1 = lambda v: (int(v[0]), int(v[1]))
+    g2 = lambda v: ((int(v[0][0]), int(v[0][1])), (int(v[1][0]), int(v[1][1])))
+    e = o.pairing(g1(vk["vk_alpha_1"]), g2(vk["vk_beta_2"]))
+    ab = vk["vk_alphabeta_12"]
+    want = [0] * 12
+    for (h, k), i in zip(((0, 0), (0, 1), (0, 2), (1, 0), (1, 1), (1, 2)), (0, 2, 4, 1, 3, 5)):   # coefficient of w^i
+        x, y = int(ab[h][k][0]), int(ab[h][k][1])                                               # (x + y u) w^i, u = w^6 - 9
+        want[i] = (want[i] + x - 9 * y) % o.P
+        want[i + 6] = (want[i + 6] + y) % o.P
+    u = o.BN_U
+    assert o.fq12_pow(e, 2 * u * (6 * u * u + 3 * u + 1)) == tuple(want)
+    assert o.fq12_pow(tuple(want), o.R) == o.FQ12_ONE and tuple(want) != o.FQ12_ONE
