@@ -25,7 +25,8 @@ Pinning (see tests/test_oracle_golden.py): Montgomery byte goldens of Fq one / G
 G2 gen (ark-circom/src/zkey.rs:417-455); the 128-byte golden proof
 zk-cli/test-circuits/sha256/proof.bin decodes to exactly the coordinates printed in
 zk-cli/README.md:82 (x, y-sign flags, Fq2 ordering); snarkjs proof/vk fixtures verify
-under the pairing here (fixtures/million/*.json); a proof produced by `groth16_prove`
+under the pairing here (fixtures/million/*.json) and the pairing value itself matches snarkjs'
+`vk_alphabeta_12` (= e(alpha, beta)^(2u(6u^2+3u+1)), ffjavascript's hard-part multiple); a proof produced by `groth16_prove`
 from the snarkjs-made complex-circuit-10000-10000.zkey verifies against that zkey's vk.
 MSM and NTT outputs have no absolute vector in the reference (its own tests are
 differential against arkworks); they are pinned through those end-to-end checks and
