@@ -62,3 +62,115 @@ def d_ifft(peval_share, rearrange: bool, pad: int, degree2: bool, dom, pp=None, 
            sid: MultiplexedStreamID = MultiplexedStreamID.Zero) -> np.ndarray:
     size = dom.size() if hasattr(dom, "size") and callable(dom.size) else dom
     return _run(peval_share, rearrange, pad, size, net, sid, inverse=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The n-party protocol itself: what `d_fft` / `d_ifft` do when the vector is packed-secret-shared over
+# n = 4l parties, all parties simulated in this process the way the reference's LocalTestNet does
+# (mpc-net/src/multi.rs:289-316).  Field arithmetic goes through the CUDA library (`Net.field_op`, the sharing's transforms).
+# ---------------------------------------------------------------------------------------------------------------------
+_FR = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+_R_MONT = (1 << 256) % _FR
+
+
+def _mont_limbs(values) -> np.ndarray:
+    out = np.zeros((len(values), 4), dtype=np.uint64)
+    for i, v in enumerate(values):
+        m = (int(v) % _FR) * _R_MONT % _FR
+        for k in range(4):
+            out[i, k] = (m >> (64 * k)) & 0xFFFFFFFFFFFFFFFF
+    return out
+
+
+def _butterfly(net, x, y, factors):
+    """(x + y f, x - y f) on (rows, 4) limb arrays."""
+    yf = net.field_op(1, 0, y, factors)
+    return net.field_op(1, 1, x, yf), net.field_op(1, 2, x, yf)
+
+
+def _fft1_in_place(px: np.ndarray, dom_size: int, l: int, gen: int, net) -> np.ndarray:
+    """`fft1_in_place` (dfft/mod.rs:98-140): the stages every party runs on its own share vector.  The twiddle of
+    column k is factor_stride^(k+1) -- the reference starts `factor` at `factor_stride`, not 1 (its final
+    `rotate_right(1)` in fft2 undoes the shift)."""
+    px = px.copy()
+    log_l, log_n = l.bit_length() - 1, dom_size.bit_length() - 1
+    for i in range(log_n, log_l, -1):
+        ps = dom_size >> i
+        stride = pow(gen, 1 << (i - 1), _FR)
+        nj = (1 << (i - 1)) // l
+        f = _mont_limbs([pow(stride, k + 1, _FR) for k in range(ps)])
+        v = px.reshape(nj, 2, ps, 4)
+        x = np.ascontiguousarray(v[:, 0]).reshape(-1, 4)
+        y = np.ascontiguousarray(v[:, 1]).reshape(-1, 4)
+        s, d = _butterfly(net, x, y, np.tile(f, (nj, 1)))
+        v[:, 0] = s.reshape(nj, ps, 4)
+        v[:, 1] = d.reshape(nj, ps, 4)
+    return px
+
+
+def _fft2_in_place(s1: np.ndarray, dom_size: int, l: int, gen: int, net) -> np.ndarray:
+    """`fft2_in_place` (dfft/mod.rs:142-182): the last log2(l) stages, run by the king on the unpacked values."""
+    log_l = l.bit_length() - 1
+    for i in range(log_l, 0, -1):
+        ps = dom_size >> i
+        stride = pow(gen, 1 << (i - 1), _FR)
+        half = 1 << (i - 1)
+        f = _mont_limbs([pow(stride, k + 1, _FR) for k in range(ps)])
+        v = s1.reshape(ps, half, 2, 4)                           # s1[k * 2^i + 2j + b]
+        x = np.ascontiguousarray(v[:, :, 0]).reshape(-1, 4)
+        y = np.ascontiguousarray(v[:, :, 1]).reshape(-1, 4)
+        s, d = _butterfly(net, x, y, np.repeat(f, half, axis=0))
+        s2 = np.empty_like(s1)
+        s2[: ps * half] = s                                      # s2[k * 2^(i-1) + j]
+        s2[ps * half:] = d                                       # s2[(k + ps) * 2^(i-1) + j]
+        s1 = s2
+    return np.roll(s1, 1, axis=0)                                # rotate_right(1)
+
+
+def _fft2_with_rearrange_pad(shares, rearrange, pad, degree2, dom_size, pp, gen, net):
+    """`fft2_with_rearrange_pad` (dfft/mod.rs:184-256): every party sends its vector to the king, who unpacks element by
+    element, finishes the transform, pads / rearranges and deals fresh packed shares back."""
+    mbyl = shares[0].shape[0]
+    s1 = np.zeros((mbyl * pp.l, 4), dtype=np.uint64)
+    for i in range(mbyl):
+        col = np.stack([sh[i] for sh in shares])                 # transpose(all_shares)[i]
+        s1[i * pp.l:(i + 1) * pp.l] = pp.unpack2(col) if degree2 else pp.unpack(col)
+    s1 = _fft2_in_place(s1, dom_size, pp.l, gen, net)
+    if pad > 1:
+        s1 = np.concatenate([s1, np.zeros(((pad - 1) * s1.shape[0], 4), dtype=np.uint64)])
+    n_out = s1.shape[0] // pp.l
+    if rearrange:
+        s1 = fft_in_place_rearrange(s1)
+        packed = [pp.pack_from_public(s1[i::n_out]) for i in range(n_out)]
+    else:
+        packed = [pp.pack_from_public(s1[i * pp.l:(i + 1) * pp.l]) for i in range(n_out)]       # pack_vec
+    return [np.stack([packed[i][p] for i in range(n_out)]) for p in range(pp.n)]
+
+
+def _dom_gen(dom_size: int) -> int:
+    return pow(5, (_FR - 1) // dom_size, _FR)
+
+
+def d_fft_mpc(pcoeff_shares, rearrange: bool, pad: int, degree2: bool, dom, pp, net) -> list:
+    """All pp.n parties of `d_fft` (dfft/mod.rs:17-54) in one process: pcoeff_shares[p] is party p's share vector
+    (dom.size() / pp.l elements, Montgomery limbs); returns the n output share vectors."""
+    size = dom.size() if hasattr(dom, "size") and callable(dom.size) else int(dom)
+    shares = [np.ascontiguousarray(s, dtype=np.uint64).reshape(-1, 4) for s in pcoeff_shares]
+    if len(shares) != pp.n or any(s.shape[0] * pp.l != size for s in shares):
+        raise MpcNetError("BadInput", "Mismatch of size in FFT, %d, %d." % (shares[0].shape[0] * pp.l, size))
+    gen = _dom_gen(size)
+    shares = [_fft1_in_place(s, size, pp.l, gen, net) for s in shares]
+    return _fft2_with_rearrange_pad(shares, rearrange, pad, degree2, size, pp, gen, net)
+
+
+def d_ifft_mpc(peval_shares, rearrange: bool, pad: int, degree2: bool, dom, pp, net) -> list:
+    """All pp.n parties of `d_ifft` (dfft/mod.rs:56-95): scale by 1/size, then the same two phases with the inverse root."""
+    size = dom.size() if hasattr(dom, "size") and callable(dom.size) else int(dom)
+    shares = [np.ascontiguousarray(s, dtype=np.uint64).reshape(-1, 4) for s in peval_shares]
+    if len(shares) != pp.n or any(s.shape[0] * pp.l != size for s in shares):
+        raise MpcNetError("BadInput", "Mismatch of size in IFFT, %d, %d." % (shares[0].shape[0] * pp.l, size))
+    gen = pow(_dom_gen(size), -1, _FR)
+    ninv = _mont_limbs([pow(size, -1, _FR)])
+    shares = [net.field_op(1, 0, s, np.tile(ninv, (s.shape[0], 1))) for s in shares]
+    shares = [_fft1_in_place(s, size, pp.l, gen, net) for s in shares]
+    return _fft2_with_rearrange_pad(shares, rearrange, pad, degree2, size, pp, gen, net)
