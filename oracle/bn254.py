@@ -28,9 +28,10 @@ zk-cli/README.md:82 (x, y-sign flags, Fq2 ordering); snarkjs proof/vk fixtures v
 under the pairing here (fixtures/million/*.json) and the pairing value itself matches snarkjs'
 `vk_alphabeta_12` (= e(alpha, beta)^(2u(6u^2+3u+1)), ffjavascript's hard-part multiple); a proof produced by `groth16_prove`
 from the snarkjs-made complex-circuit-10000-10000.zkey verifies against that zkey's vk.
-MSM and NTT outputs have no absolute vector in the reference (its own tests are
-differential against arkworks); they are pinned through those end-to-end checks and
-through naive-definition cross-checks.
+MSM and NTT outputs have no absolute vector of their own in the reference (its tests are
+differential against arkworks); they are pinned end to end: oracle/ark_rand.py regenerates the
+reference's seeded setup and the prover built on this module's arithmetic (C++ twin) returns the
+reference's committed proof.bin bit for bit (tests/test_oracle_reference_proof.py).
 """
 from __future__ import annotations
 

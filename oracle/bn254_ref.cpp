@@ -531,6 +531,20 @@ static Jac<F> aff_to_jac(const Aff<F>& a) {
     return {a.x, a.y, F::one()};
 }
 
+// out[i] = scalars[i] * base (affine, Montgomery limbs): what `FixedBase::msm(.., g1_table, scalars)` yields in
+// ark-groth16's generator (third-party; restated from its contract) -- used to rebuild the reference's proving key from
+// the regenerated toxic waste (oracle/ark_rand.py).  Plain double-and-add per scalar, OpenMP over the scalars.
+template <class F>
+static void fixed_base_mul(const u64* base, const u64* scalars, size_t n, u64* out, int nthreads) {
+    const int PL = 2 * Limbs<F>::N;
+    Jac<F> g = aff_to_jac(load_affine<F>(base));
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 64)
+    for (long long i = 0; i < (long long)n; ++i) {
+        Aff<F> a = jac_to_affine(jac_mul_fr(g, scalars + 4 * (size_t)i));
+        store_affine<F>(out + (size_t)PL * i, a);
+    }
+}
+
 extern "C" {
 
 int orc_num_threads(void) { return resolve_threads(0); }
@@ -558,6 +572,13 @@ void orc_field_op(int field, int op, const u64* a, const u64* b, u64* out) {
                       case 3: r = x.inv(); break; case 4: r = x.to_mont(); break; default: r = x.from_mont(); }
         memcpy(out, r.l, 32);
     }
+}
+
+void orc_g1_fixed_base_mul(const u64* base, const u64* scalars, size_t n, u64* out, int nthreads) {
+    ensure_init(); fixed_base_mul<Fq>(base, scalars, n, out, resolve_threads(nthreads));
+}
+void orc_g2_fixed_base_mul(const u64* base, const u64* scalars, size_t n, u64* out, int nthreads) {
+    ensure_init(); fixed_base_mul<Fq2>(base, scalars, n, out, resolve_threads(nthreads));
 }
 
 void orc_g1_generate(u64 seed, size_t n, u64* out, int nthreads) { ensure_init(); gen_points<Fq>(G1GEN, seed, n, out, resolve_threads(nthreads)); }

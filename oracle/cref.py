@@ -69,6 +69,17 @@ def g2_generate(seed: int, n: int, nthreads: int = 0) -> np.ndarray:
     return out
 
 
+def fixed_base_mul(base, scalars, g2: bool = False, nthreads: int = 0) -> np.ndarray:
+    """scalars[i] * base for one affine base point (Montgomery limbs) and (n, 4) Montgomery scalars."""
+    w = 16 if g2 else 8
+    b = np.ascontiguousarray(base, dtype=np.uint64).reshape(w)
+    s = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros((s.shape[0], w), dtype=np.uint64)
+    fn = lib().orc_g2_fixed_base_mul if g2 else lib().orc_g1_fixed_base_mul
+    fn(_p(b), _p(s), ctypes.c_size_t(s.shape[0]), _p(out), int(nthreads))
+    return out
+
+
 def fr_generate(seed: int, n: int) -> np.ndarray:
     out = np.zeros((n, 4), dtype=np.uint64)
     lib().orc_fr_generate(ctypes.c_uint64(seed), ctypes.c_size_t(n), _p(out))

@@ -1,0 +1,33 @@
+"""BASELINE config 4 on the GPU: the proving key of the reference's seeded setup (regenerated on the CPU by
+oracle/ark_rand.py + the C++ twin, see tests/test_oracle_reference_proof.py) goes through the product's public API and the
+128 bytes that come back must be the reference's own committed proof, `zk-cli/test-circuits/sha256/proof.bin`.
+(Runs last in the GPU suite; written at the end of round 1 after the GPU budget was spent, so its first execution is the
+round-end run -- every call it makes is one the earlier tests already exercise on the same circuit shape.)"""
+import os
+
+import numpy as np
+import pytest
+
+from distributed_groth16_b200 import ark_serialize as ark
+from distributed_groth16_b200.groth16 import ProvingKey, prove, verify
+from test_oracle_reference_proof import G, reference_sha256_instance
+
+pytestmark = pytest.mark.gpu
+
+
+def test_gpu_prover_reproduces_the_reference_proof_bin(net, cref):
+    gold = open(os.path.join(G, "sha256_proof.bin"), "rb").read()
+    pk, vk, z, a, b, c, (n_vars, n_inputs, m) = reference_sha256_instance(cref)
+    gpk = ProvingKey(net, pk["a_query"], pk["b_g1_query"], pk["b_g2_query"], pk["l_query"], pk["h_query"], n_inputs,
+                     vk["alpha_g1"], vk["beta_g1"], vk["delta_g1"], vk["beta_g2"], vk["delta_g2"])
+    try:
+        assert prove.create_proof(gpk, z, a, b, c) == gold
+        assert gpk.precompute(None) == 0                              # and without the fixed-base tables
+        assert prove.create_proof(gpk, z, a, b, c) == gold
+    finally:
+        gpk.free()
+    avk = ark.ArkVerifyingKey(vk["alpha_g1"], vk["beta_g2"], vk["gamma_g2"], vk["delta_g2"], vk["gamma_abc_g1"])
+    assert verify.verify_proof(net, avk, z[1:n_inputs], gold)
+    bad = np.array(z[1:n_inputs], copy=True)
+    bad[0, 0] ^= np.uint64(1)
+    assert not verify.verify_proof(net, avk, bad, gold)
