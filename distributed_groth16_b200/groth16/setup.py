@@ -47,6 +47,24 @@ def _fixed_base(net, scalars, g2=False):
     return out
 
 
+def _fixed_base_custom(net, base, scalars, g2=False):
+    """scalars[i] * base for an arbitrary base point (the reference draws its generators at random, ark-groth16's
+    `generate_random_parameters_with_reduction`): `b200zk_points_matmul_dev` with a one-point chunk, i.e. one thread per
+    scalar, in slabs of 4096 rows (its limit).  One-off setup work."""
+    import torch
+    n, w = int(scalars.shape[0]), 16 if g2 else 8
+    out = torch.empty((n, w), dtype=torch.int64, device=scalars.device)
+    pt = net.to_device(np.ascontiguousarray(base, dtype=np.uint64).reshape(1, w))
+    scalars = scalars.contiguous()
+    for lo in range(0, n, 4096):
+        rows = min(4096, n - lo)
+        net.check(net._lib.b200zk_points_matmul_dev(net._h, 0, int(g2), c_vp(pt.data_ptr()), 1, 1,
+                                                    c_vp(scalars[lo:lo + rows].data_ptr()), rows,
+                                                    c_vp(out[lo:lo + rows].data_ptr())))
+    net.sync(0)
+    return out
+
+
 def _powers(net, base: int, scale: int, n: int):
     import torch
     out = torch.empty((n, 4), dtype=torch.int64, device=torch.device("cuda", net.device))
@@ -71,9 +89,11 @@ def _transpose_csr(net, rows, cols, vals_dev_order, n_cols, extra=None):
 
 
 def circuit_specific_setup(net, n_vars: int, n_inputs: int, num_constraints: int, a_coo, b_coo, c_coo, toxic,
-                           values_montgomery_depth: int = -1):
+                           values_montgomery_depth: int = -1, g1_generator=None, g2_generator=None):
     """a_coo / b_coo / c_coo: (rows, cols, vals (nnz, 4) u64) of the R1CS matrices; toxic = (tau, alpha, beta, gamma, delta)
-    canonical ints.  Returns (ProvingKey on the device, VerifyingKey as host limb arrays, ConstraintMatrices)."""
+    canonical ints.  g1_generator / g2_generator: affine Montgomery limbs (8 / 16 u64) of the group elements every query
+    is a multiple of -- ark-groth16 draws them at random (`E::G1::rand(rng)`), None = the standard generators.
+    Returns (ProvingKey on the device, VerifyingKey as host limb arrays, ConstraintMatrices)."""
     import torch
     tau, alpha, beta, gamma, delta = (int(x) % R for x in toxic)
     m = 1
@@ -123,15 +143,20 @@ def circuit_specific_setup(net, n_vars: int, n_inputs: int, num_constraints: int
     hs = _powers(net, tau, pow(delta, -1, R), 2 * m)
     hs[2 * m - 1] = 0
     hs = net.ntt_dev(hs, inverse=True)[1::2].contiguous()
-    a_query = _fixed_base(net, a_t)
-    b_g1_query = _fixed_base(net, b_t)
-    b_g2_query = _fixed_base(net, b_t, g2=True)
-    l_query = _fixed_base(net, l_all[n_inputs:].contiguous())
-    h_query = _fixed_base(net, hs)
-    ic = _fixed_base(net, ic_all[:n_inputs].contiguous())
+    custom = g1_generator is not None or g2_generator is not None
+    if custom and (g1_generator is None or g2_generator is None):
+        raise ValueError("give both generators or neither")
+    _fb = (lambda sc, g2=False: _fixed_base_custom(net, g2_generator if g2 else g1_generator, sc, g2)) if custom else \
+        (lambda sc, g2=False: _fixed_base(net, sc, g2))
+    a_query = _fb(a_t)
+    b_g1_query = _fb(b_t)
+    b_g2_query = _fb(b_t, g2=True)
+    l_query = _fb(l_all[n_inputs:].contiguous())
+    h_query = _fb(hs)
+    ic = _fb(ic_all[:n_inputs].contiguous())
     consts = torch.from_numpy(np.stack([_mont_limbs(v) for v in (alpha, beta, delta, gamma)]).view(np.int64)).to(dev)
-    g1c = _fixed_base(net, consts).cpu().numpy().view(np.uint64)          # alpha, beta, delta, gamma in G1
-    g2c = _fixed_base(net, consts, g2=True).cpu().numpy().view(np.uint64)
+    g1c = _fb(consts).cpu().numpy().view(np.uint64)          # alpha, beta, delta, gamma in G1
+    g2c = _fb(consts, g2=True).cpu().numpy().view(np.uint64)
     vk_points = np.concatenate([g1c[0], g1c[1], g1c[2], g2c[1], g2c[2]])
     pk = ProvingKey.from_device(net, a_query, b_g1_query, b_g2_query, l_query, h_query, n_inputs, vk_points)
     vk = VerifyingKey(alpha_g1=g1c[0], beta_g2=g2c[1], gamma_g2=g2c[3], delta_g2=g2c[2],

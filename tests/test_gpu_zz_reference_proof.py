@@ -31,3 +31,34 @@ def test_gpu_prover_reproduces_the_reference_proof_bin(net, cref):
     bad = np.array(z[1:n_inputs], copy=True)
     bad[0, 0] ^= np.uint64(1)
     assert not verify.verify_proof(net, avk, bad, gold)
+
+
+def test_gpu_setup_from_the_reference_seed_then_gpu_proof_is_the_reference_proof_bin(net, cref):
+    """The whole pipeline on the GPU: R1CS + the seed's toxic waste and generators -> `circuit_specific_setup` (fixed-base
+    multiplications of the *drawn* generators) -> GPU qap / h / prove -> the reference's proof.bin; the GPU-made
+    verifying key equals the CPU-regenerated one limb for limb."""
+    from oracle import ark_rand as ar, layout
+    from distributed_groth16_b200.groth16 import circom, setup
+    from test_oracle_reference_proof import SEED
+    gold = open(os.path.join(G, "sha256_proof.bin"), "rb").read()
+    d = np.load(os.path.join(G, "sha256_circuit.npz"))
+    n_wires, n_pub, n_cons = (int(x) for x in d["dims"])
+    n_inputs = n_pub + 1
+    m = 1
+    while m < n_cons + n_inputs:
+        m <<= 1
+    tw = ar.groth16_toxic_waste(SEED, m)
+    coo = lambda k: (d[k + "_rows"], d[k + "_cols"], d[k + "_vals"])
+    pk, vk, mats = setup.circuit_specific_setup(
+        net, n_wires, n_inputs, n_cons, coo("a"), coo("b"), coo("c"),
+        (tw["t"], tw["alpha"], tw["beta"], tw["gamma"], tw["delta"]),
+        g1_generator=layout.g1_to_arr([tw["g1"]])[0], g2_generator=layout.g2_to_arr([tw["g2"]])[0])
+    try:
+        z = net.fr_convert(net.to_device(d["witness"]), to_mont=True)
+        zero = np.zeros(4, dtype=np.uint64)
+        assert circom.prove_from_matrices(pk, mats, z, zero, zero) == gold
+    finally:
+        pk.free()
+    _, want_vk, *_ = reference_sha256_instance(cref)
+    for name in ("alpha_g1", "beta_g2", "gamma_g2", "delta_g2", "gamma_abc_g1"):
+        assert (np.asarray(getattr(vk, name)).reshape(-1) == np.asarray(want_vk[name]).reshape(-1)).all(), name
