@@ -206,9 +206,13 @@ def _claim_stdout():
     code on fd 1): keep a private duplicate of fd 1 for the JSON line and point fd 1 at stderr for everything else."""
     global _JSON_FD
     if _JSON_FD is None:
-        sys.stdout.flush()
-        _JSON_FD = os.dup(1)
-        os.dup2(2, 1)
+        try:
+            sys.stdout.flush()
+            fd = os.dup(1)
+            os.dup2(2, 1)
+            _JSON_FD = fd
+        except OSError:                 # no usable stderr: keep the plain stdout
+            _JSON_FD = None
 
 
 def emit(obj):
