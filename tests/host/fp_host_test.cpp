@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include "../../distributed_groth16_b200/csrc/fp.cuh"
 #include "../../distributed_groth16_b200/csrc/ec.cuh"
+#include "../../distributed_groth16_b200/csrc/ec29.cuh"
 
 extern "C" void orc_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out);
 extern "C" void orc_fr_generate(uint64_t seed, size_t n, uint64_t* out);
@@ -113,12 +114,89 @@ static int test_curve(const char* name, int is_g2) {
     return bad;
 }
 
+
+// ---- fp29.cuh / ec29.cuh: the 9 x 29-bit carry-free field and the bucket group law built on it ----------------------
+template <class P, int FIELD>
+static int test_field29(const char* name) {
+    typedef Fp<P> F;
+    typedef Fp29<P> G;
+    int fails = 0;
+    const int N = 20000;
+    for (int it = 0; it < N; ++it) {
+        uint64_t buf[8];
+        orc_fr_generate(rnd(), 2, buf);
+        F a, b; memcpy(a.l, buf, 32); memcpy(b.l, buf + 4, 32);
+        if (FIELD == 0) { a.l[7] &= 0x0FFFFFFFu; b.l[7] &= 0x0FFFFFFFu; }
+        if (it == 0) a = F::zero();
+        if (it == 1) b = F::zero();
+        if (it == 2) { a = F::neg(F::one()); b = a; }                       // p - R: large canonical values
+        if (it == 3) { a = F::zero(); a.l[0] = 1; a = F::neg(a); b = a; }   // p - 1, the largest canonical integer
+        G ga = G::from_mont256(a), gb = G::from_mont256(b);
+        F r;
+        r = G::to_mont256(G::mul(ga, gb)); if (r != F::mul(a, b)) { if (fails++ < 5) printf("%s mul29 mismatch it=%d\n", name, it); }
+        r = G::to_mont256(G::sqr(ga)); if (r != F::mul(a, a)) { if (fails++ < 5) printf("%s sqr29 mismatch it=%d\n", name, it); }
+        r = G::to_mont256(G::norm(G::add_lazy(ga, gb))); if (r != F::add(a, b)) { if (fails++ < 5) printf("%s add29 mismatch it=%d\n", name, it); }
+        {   // subtraction needs value(b) < K p: reduce the operands below 2 p first (x * 1)
+            G ra = G::mul(ga, G::one()), rb = G::mul(gb, G::one());
+            r = G::to_mont256(G::template sub<2>(ra, rb)); if (r != F::sub(a, b)) { if (fails++ < 5) printf("%s sub29 mismatch it=%d\n", name, it); }
+            G lz = G::template sub_lazy<4, 31>(ra, G::add_lazy(rb, G::dbl_lazy(rb)));     // a - 3 b + 4 p  (2 + 2 * 2 ... uses < 3.6 p)
+            r = G::to_mont256(G::norm(lz)); if (r != F::sub(a, F::add(b, F::dbl(b)))) { if (fails++ < 5) printf("%s sub_lazy<.,31> mismatch it=%d\n", name, it); }
+            r = G::to_mont256(G::norm(G::template neg_lazy<2, 29>(rb))); if (r != F::neg(b)) { if (fails++ < 5) printf("%s neg29 mismatch it=%d\n", name, it); }
+            // mixed-domain product: 2^261-domain x (plain re-limbed 2^256-domain) lands in the 2^256 domain
+            r = G::canon256(G::mul(ga, G::relimb(b))); if (r != F::mul(a, b)) { if (fails++ < 5) printf("%s mixed mul mismatch it=%d\n", name, it); }
+            bool z = G::mul(ra, rb).is_zero_mod_2p();
+            if (z != (a.is_zero() || b.is_zero())) { if (fails++ < 5) printf("%s zero test mismatch it=%d\n", name, it); }
+        }
+    }
+    printf("%s (29-bit limbs): %d iterations, %d failures\n", name, N, fails);
+    return fails;
+}
+
+static int test_curve29() {
+    const int n = 64;
+    uint64_t* pts = (uint64_t*)malloc(n * 64);
+    orc_g1_generate(4242, n, pts, 1);
+    int fails = 0;
+    for (int round = 0; round < 50; ++round) {
+        xyzz_t<Fq> ref = xyzz_t<Fq>::identity();
+        xyzz29_g1 acc = xyzz29_g1::identity();
+        for (int step = 0; step < 40; ++step) {
+            uint64_t r = rnd();
+            affine_t<Fq> p; memcpy(&p, pts + 8 * (r % n), 64);
+            bool neg = (r >> 20) & 1;
+            if (step == 7) p = affine_t<Fq>::infinity();
+            if (round % 5 == 1 && step == 1) { memcpy(&p, pts + 8 * 3, 64); neg = false; }      // P + P right after the first point
+            if (round % 5 == 1 && step == 0) { memcpy(&p, pts + 8 * 3, 64); neg = false; }
+            if (round % 5 == 2 && step == 0) { memcpy(&p, pts + 8 * 4, 64); neg = true; }       // -P then +P: identity, then keep going
+            if (round % 5 == 2 && step == 1) { memcpy(&p, pts + 8 * 4, 64); neg = false; }
+            if (round % 5 == 3 && step == 20) {   // acc == +-p deep inside a chain: add the current sum itself
+                affine_t<Fq> cur = xyzz_t<Fq>::to_affine(ref);
+                p = cur; neg = (round & 1) != 0;
+            }
+            xyzz_t<Fq>::madd(ref, p, neg);
+            xyzz29_g1::madd(acc, p, neg);
+            xyzz_t<Fq> got = xyzz29_g1::to_xyzz(acc);
+            affine_t<Fq> ga = xyzz_t<Fq>::to_affine(got), ra = xyzz_t<Fq>::to_affine(ref);
+            if (memcmp(&ga, &ra, sizeof(ga)) || got.is_inf() != ref.is_inf()) {
+                if (fails++ < 5) printf("G1 (29-bit limbs): madd mismatch round %d step %d\n", round, step);
+                break;
+            }
+        }
+    }
+    printf("G1 (29-bit limbs) bucket group law: %d failures\n", fails);
+    free(pts);
+    return fails;
+}
+
 int main() {
     int fails = 0;
     fails += test_field<Fq, 0>("Fq");
     fails += test_field<Fr, 1>("Fr");
     fails += test_curve<G1Curve>("G1", 0);
     fails += test_curve<G2Curve>("G2", 1);
+    fails += test_field29<FqParams, 0>("Fq");
+    fails += test_field29<FrParams, 1>("Fr");
+    fails += test_curve29();
     printf(fails ? "FAILED\n" : "ALL OK\n");
     return fails ? 1 : 0;
 }

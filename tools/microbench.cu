@@ -2,7 +2,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench tools/microbench.cu
 #include <cstdio>
 #include <cuda_runtime.h>
-#include "../distributed_groth16_b200/csrc/ec.cuh"
+#include "../distributed_groth16_b200/csrc/ec29.cuh"
 using namespace b200zk;
 
 #define ITERS 2000
@@ -87,6 +87,50 @@ __global__ void __launch_bounds__(128) k_madd_chain(xyzz_t<Fq>* out, int iters) 
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
+// ---- 9 x 29-bit carry-free field (fp29.cuh): operands come from memory so nothing is constant-folded ----
+__global__ void k_mul29_chain(const Fq* in, Fq* out, int iters) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    Fq29 a = Fq29::from_mont256(in[t & 1023]), b = Fq29::from_mont256(in[(t + 1) & 1023]);
+    for (int it = 0; it < iters; ++it) a = Fq29::mul(a, b);
+    out[t] = Fq29::to_mont256(a);
+}
+__global__ void k_sqr29_chain(const Fq* in, Fq* out, int iters) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    Fq29 a = Fq29::from_mont256(in[t & 1023]);
+    for (int it = 0; it < iters; ++it) a = Fq29::sqr(a);
+    out[t] = Fq29::to_mont256(a);
+}
+__global__ void k_mul32_chain_mem(const Fq* in, Fq* out, int iters) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    Fq x = in[t & 1023], y = in[(t + 1) & 1023];
+    for (int it = 0; it < iters; ++it) x = Fq::mul(x, y);
+    out[t] = x;
+}
+__global__ void __launch_bounds__(128, 4) k_madd29_chain(const affine_t<Fq>* pts, xyzz_t<Fq>* out, int iters) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    xyzz29_g1 acc = xyzz29_g1::identity();
+    for (int it = 0; it < iters; ++it) xyzz29_g1::madd(acc, pts[(t * 7 + it) & 1023], (it & 3) == 1);
+    out[t] = xyzz29_g1::to_xyzz(acc);
+}
+__global__ void __launch_bounds__(128, 4) k_madd32_chain_mem(const affine_t<Fq>* pts, xyzz_t<Fq>* out, int iters) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    xyzz_t<Fq> acc = xyzz_t<Fq>::identity();
+    for (int it = 0; it < iters; ++it) xyzz_t<Fq>::madd(acc, pts[(t * 7 + it) & 1023], (it & 3) == 1);
+    out[t] = acc;
+}
+// 1024 distinct curve points k G, k = 1..1024 (running sum), and 1024 field elements (their x coordinates)
+__global__ void k_make_points(affine_t<Fq>* pts) {
+    if (threadIdx.x || blockIdx.x) return;
+    affine_t<Fq> g;
+    for (int i = 0; i < 8; ++i) { g.x.l[i] = CurveConst::g1_gen_x(i); g.y.l[i] = CurveConst::g1_gen_y(i); }
+    xyzz_t<Fq> acc = xyzz_t<Fq>::identity();
+    for (int i = 0; i < 1024; ++i) { xyzz_t<Fq>::madd(acc, g, false); pts[i] = xyzz_t<Fq>::to_affine(acc); }
+}
+__global__ void k_cmp(const uint32_t* a, const uint32_t* b, size_t n, int* bad) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n && a[i] != b[i]) atomicAdd(bad, 1);
+}
+
 template <class K>
 static float timeit(K launch) {
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
@@ -129,5 +173,31 @@ int main() {
     printf("madd chain x2occ: %.3f ms  %.2f Gmadd/s\n", ms, (double)sms * 8 * 128 * 500 / ms / 1e6);
     ms = timeit([&] { k_madd_chain<<<1, 32>>>((xyzz_t<Fq>*)buf, 500); });
     printf("madd latency    : single warp: %.1f ns per dependent madd\n", ms * 1e6 / 500);
+    // ---- 29-bit-limb field vs the 32-bit-limb one, same operands from memory ----
+    affine_t<Fq>* pts; cudaMalloc(&pts, 1024 * sizeof(affine_t<Fq>));
+    k_make_points<<<1, 32>>>(pts); cudaDeviceSynchronize();
+    void* buf2; cudaMalloc(&buf2, (size_t)sms * 8 * 1024 * 256);
+    int* bad; cudaMalloc(&bad, 4); cudaMemset(bad, 0, 4);
+    const Fq* fin = (const Fq*)pts;
+    for (int t : {128, 256}) {
+        int bl = sms * (t == 128 ? 8 : 4);
+        ms = timeit([&] { k_mul32_chain_mem<<<bl, t>>>(fin, (Fq*)buf, iters); });
+        printf("Fq::mul (32-bit limbs, mem operands) blocks %d x %d: %.3f ms  %.1f Gmul/s\n", bl, t, ms, (double)bl * t * iters / ms / 1e6);
+        ms = timeit([&] { k_mul29_chain<<<bl, t>>>(fin, (Fq*)buf2, iters); });
+        printf("Fq29::mul (29-bit limbs)             blocks %d x %d: %.3f ms  %.1f Gmul/s\n", bl, t, ms, (double)bl * t * iters / ms / 1e6);
+        k_cmp<<<(unsigned)(((size_t)bl * t * 8 + 255) / 256), 256>>>((uint32_t*)buf, (uint32_t*)buf2, (size_t)bl * t * 8, bad);
+        ms = timeit([&] { k_sqr29_chain<<<bl, t>>>(fin, (Fq*)buf2, iters); });
+        printf("Fq29::sqr                            blocks %d x %d: %.3f ms  %.1f Gsqr/s\n", bl, t, ms, (double)bl * t * iters / ms / 1e6);
+    }
+    for (int occ : {4, 8}) {
+        ms = timeit([&] { k_madd32_chain_mem<<<sms * occ, 128>>>(pts, (xyzz_t<Fq>*)buf, 500); });
+        printf("madd 32-bit limbs x%d blocks/SM: %.3f ms  %.2f Gmadd/s\n", occ, ms, (double)sms * occ * 128 * 500 / ms / 1e6);
+        ms = timeit([&] { k_madd29_chain<<<sms * occ, 128>>>(pts, (xyzz_t<Fq>*)buf2, 500); });
+        printf("madd 29-bit limbs x%d blocks/SM: %.3f ms  %.2f Gmadd/s\n", occ, ms, (double)sms * occ * 128 * 500 / ms / 1e6);
+    }
+    int hbad = 0; cudaMemcpy(&hbad, bad, 4, cudaMemcpyDeviceToHost);
+    printf("mul29 == mul32 on %d-thread chains: %s (%d words differ)\n", sms * 8 * 128, hbad ? "MISMATCH" : "ok", hbad);
+    cudaError_t e = cudaDeviceSynchronize();
+    printf("cuda status: %s\n", cudaGetErrorString(e));
     return 0;
 }
