@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 
 LOG_N = int(os.environ.get("B200ZK_BENCH_LOG_N", "20"))
 METRIC = "G1 MSM throughput (BN254 Pippenger, 2^%d pairs per GPU)" % LOG_N
+WORKLOAD = "BN254 G1 Pippenger MSM 2^%d random scalar/point pairs per GPU" % LOG_N     # same string in both arms
 UNIT = "Mpairs/s"
 ALG_BYTES_PER_PAIR = 96.0       # 32 B scalar + 64 B affine point, each read once
 
@@ -108,7 +109,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32x8 Montgomery (256-bit modular integers)", "data": "synthetic",
-        "config": {"workload": "BN254 G1 Pippenger MSM 2^%d random scalar/point pairs" % LOG_N,
+        "config": {"workload": WORKLOAD,
                    "note": "CPU restatement of arkworks VariableBaseMSM (oracle/bn254_ref.cpp); the Rust reference "
                            "cannot be built in this image"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -250,8 +251,6 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("B200ZK_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"        # NCCL prints its banner on stdout; rank 0 must print ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     warm = max(args.warmup, 3)
     n = 1 << LOG_N
@@ -414,9 +413,13 @@ def main():
         return
 
     peak, peak_src = _peaks()
-    acc = rep.get("msm_accumulate_g1", {"launches": 1, "ms": float("nan")})
-    acc_ms = acc["ms"] / max(acc["launches"], 1)
-    achieved = ALG_BYTES_PER_PAIR * n / (acc_ms * 1e-3) / 1e9
+    # the bucket kernel runs once per window group (msm.cu, window-group pipeline): each launch processes 1/G of every
+    # pair's digits, i.e. 96 n / G algorithmic bytes, in 1/G of the step's bucket time -- same GB/s either way
+    acc = rep.get("msm_accumulate_g1", {"launches": 5, "ms": float("nan")})
+    acc_launches_per_step = max(acc["launches"], 1) / 5.0
+    acc_ms_launch = acc["ms"] / max(acc["launches"], 1)
+    acc_ms = acc["ms"] / 5.0                                                  # per step, all launches
+    achieved = ALG_BYTES_PER_PAIR * n / acc_launches_per_step / (acc_ms_launch * 1e-3) / 1e9
     kernel_ms = {k: round(v["ms"] / 5.0, 4) for k, v in rep.items()}
     # what actually bounds the kernel: the multiplier pipe.  A 256-bit Montgomery product = 128 32-bit wide multiply-adds
     # with carry, which issue at 32 lanes/clk/SM (tools/microbench.cu, profiles/r1_microbench_pipes.txt).
@@ -432,7 +435,7 @@ def main():
         "warmup": warm, "ms_per_step": ms_step, "ms_per_step_median": ms_step_sorted[len(ms_step_sorted) // 2],
         "ms_per_step_min": ms_step_sorted[0], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32x8 Montgomery (256-bit modular integers)", "data": "synthetic",
-        "config": {"workload": "BN254 G1 Pippenger MSM 2^%d random scalar/point pairs per GPU" % LOG_N,
+        "config": {"workload": WORKLOAD,
                    "pairs_per_gpu": n, "l2": "256 MiB flush write between timed iterations; inputs+workspace > L2",
                    "parallelism": "length-sharded x%d, all-gather of XYZZ partials" % world},
         "e2e": {"value": world * n / ms_e2e / 1e3, "unit": UNIT, "ms_per_step": ms_e2e,
@@ -441,7 +444,9 @@ def main():
         "wall_s_timed_region": t_wall,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "msm_accumulate_g1", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": acc_ms,
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src, "kernel_ms": acc_ms_launch,
+                     "launches_per_step": acc_launches_per_step, "kernel_ms_per_step": acc_ms,
+                     "algorithmic_bytes_per_launch": ALG_BYTES_PER_PAIR * n / acc_launches_per_step,
                      "note": "256-bit modular integer arithmetic: IMAD-bound by construction, HBM fraction is small",
                      "pipe": pipe},
         "kernel_ms_per_step": kernel_ms,
@@ -451,7 +456,9 @@ def main():
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
-            out["roofline"]["traffic"] = json.load(open(traffic_file)).get("msm_accumulate_g1_bytes_per_launch")
+            tj = json.load(open(traffic_file))
+            out["roofline"]["traffic"] = tj.get("msm_accumulate_g1_bytes_per_launch")
+            out["roofline"]["traffic_source"] = "static: ncu --set full capture recorded in profiles/traffic.json (%s), not measured in this run" % tj.get("source", "see profiles/README.md")
         except Exception:
             pass
     if not args.no_cpu_baseline:

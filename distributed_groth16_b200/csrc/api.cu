@@ -65,6 +65,7 @@ int b200zk_ctx_create(int device, b200zk_ctx** out) {
                  cudaStreamCreateWithPriority(&ctx->lane_acc[k], cudaStreamNonBlocking, lo) == cudaSuccess;
             for (int j = 0; ok && j < 3; ++j) ok = cudaEventCreateWithFlags(&ctx->lane_ev[k][j], cudaEventDisableTiming) == cudaSuccess;
         }
+        for (int k = 0; ok && k < 6; ++k) ok = cudaStreamCreateWithPriority(&ctx->msm_side[k], cudaStreamNonBlocking, hi) == cudaSuccess;
         if (!ok) { b200zk_ctx_destroy(ctx); return B200ZK_ERR_CUDA; }
     }
     *out = ctx;
@@ -90,6 +91,8 @@ void b200zk_ctx_destroy(b200zk_ctx* ctx) {
         for (int k = 0; k < 4; ++k) if (s.stage_ev[k]) cudaEventDestroy(s.stage_ev[k]);
     }
     if (ctx->hi_stream) cudaStreamDestroy(ctx->hi_stream);
+    for (int k = 0; k < 6; ++k) if (ctx->msm_side[k]) cudaStreamDestroy(ctx->msm_side[k]);
+    for (auto& v : ctx->msm_events) for (cudaEvent_t e : v) cudaEventDestroy(e);
     for (int k = 0; k < 5; ++k) {
         if (ctx->lane_main[k]) cudaStreamDestroy(ctx->lane_main[k]);
         if (ctx->lane_acc[k]) cudaStreamDestroy(ctx->lane_acc[k]);

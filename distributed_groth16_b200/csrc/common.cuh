@@ -86,6 +86,12 @@ struct b200zk_ctx {
     std::mutex plan_mu;
     std::map<uint32_t, b200zk::NttPlan*> plans;
     void *fb_table_g1 = nullptr, *fb_table_g2 = nullptr;     // fixed-base window tables of the generators (setup.cu)
+    // MSM channels (msm.cu, window-group pipeline): 0..5 = slot i's main / aux workspace (2 i + aux), 6..10 = prove lanes.
+    // msm_side[ch]: high-priority helper stream that runs the sort phases and the reduction / Horner tail of one window
+    // group while the bucket kernel of the next group occupies the SMs; msm_events[ch]: its event pool (grown on demand,
+    // only ever touched under the owning slot's mutex).
+    cudaStream_t msm_side[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> msm_events[11];
 };
 
 struct b200zk_pk {
@@ -168,10 +174,10 @@ static inline unsigned ceil_log2(size_t n) {
 }
 
 struct MsmLane {
-    cudaStream_t st;          // digits, sort, merge, reduction, combine
+    cudaStream_t st;          // digits, sort, merge, reduction, combine (the result is ordered on this stream)
     DevBuf* ws;
     cudaStream_t acc_st;      // bucket accumulation
-    cudaEvent_t ev_sorted, ev_acc;
+    int channel;              // event pool (b200zk_ctx::msm_events)
 };
 
 // ---- entry points implemented across translation units -------------------------------------

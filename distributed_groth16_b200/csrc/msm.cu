@@ -17,7 +17,6 @@
 //   6 combine    Horner over windows (c doublings each)
 #include "common.cuh"
 #include "glv.cuh"
-#include "ec29.cuh"
 
 namespace b200zk {
 
@@ -46,7 +45,10 @@ __device__ __forceinline__ void st16(T* p, const T& v) {
 // 1. digits + histogram
 // ---------------------------------------------------------------------------------------------
 // fold != 0 (fixed-base tables, section 7): every window shares ONE bucket set, the window is carried by the
-// entry index (w * n + i selects 2^{cw} P_i in the table) instead of by the bucket index
+// entry index (w * n + i selects 2^{cw} P_i in the table) instead of by the bucket index.
+// Otherwise window w fills bucket set s = W - 1 - w: sets are numbered in the order the Horner chain consumes them (top
+// window first), so that a *group* of consecutive sets can be reduced and folded into the chain while the bucket
+// kernel of the next group is still running (host side, "window-group pipeline").
 __global__ void k_msm_digits(const Fr* scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t fold, uint32_t* keys,
                              uint32_t* ranks, uint32_t* counts) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -68,17 +70,19 @@ __global__ void k_msm_digits(const Fr* scalars, uint32_t n, uint32_t c, uint32_t
         uint32_t neg = 0;
         if (d > B) { d = (1u << c) - d; neg = 1; carry = 1; }
         if (d != 0) {
-            uint32_t g = (fold ? 0u : w * B) + (d - 1);
+            uint32_t g = (fold ? 0u : (W - 1 - w) * B) + (d - 1);
             rank = atomicAdd(counts + g, 1u);
             key = g | (neg << 31);
         }
-        keys[(size_t)w * n + i] = key;
-        ranks[(size_t)w * n + i] = rank;
+        const size_t slot = (size_t)(fold ? w : W - 1 - w) * n + i;
+        keys[slot] = key;
+        ranks[slot] = rank;
     }
 }
 
-// G1 only: k = k1 + k2 lambda (glv.cuh); the digits of |k1| fill windows [0, Wh), those of |k2| windows [Wh, 2 Wh)
-// over the same points -- phi is applied once to the second group's result in k_msm_combine_glv.
+// G1 only: k = k1 + k2 lambda (glv.cuh); window w of |k1| fills bucket set 2 (Wh - 1 - w), window w of |k2| set
+// 2 (Wh - 1 - w) + 1 over the same points (top windows first, the two halves interleaved: see k_msm_digits) -- phi is
+// applied once to the second chain's result in k_msm_horner_glv.
 __global__ void k_msm_digits_glv(const Fr* scalars, uint32_t n, uint32_t c, uint32_t Wh, uint32_t* keys, uint32_t* ranks,
                                  uint32_t* counts) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -103,11 +107,11 @@ __global__ void k_msm_digits_glv(const Fr* scalars, uint32_t n, uint32_t c, uint
             uint32_t neg = 0;
             if (d > B) { d = (1u << c) - d; neg = 1; carry = 1; }
             if (d != 0) {
-                uint32_t g = (h * Wh + w) * B + (d - 1);
+                uint32_t g = (2 * (Wh - 1 - w) + h) * B + (d - 1);
                 rank = atomicAdd(counts + g, 1u);
                 key = g | ((neg ^ sgn) << 31);
             }
-            size_t slot = (size_t)(h * Wh + w) * n + i;
+            size_t slot = (size_t)(2 * (Wh - 1 - w) + h) * n + i;
             keys[slot] = key;
             ranks[slot] = rank;
         }
@@ -183,10 +187,12 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t* out, const 
 // ---------------------------------------------------------------------------------------------
 // 3. scatter
 // ---------------------------------------------------------------------------------------------
-__global__ void k_msm_scatter(const uint32_t* keys, const uint32_t* ranks, const uint32_t* offsets, uint32_t n,
+// slots [t0, t0 + total) of keys / ranks (one window group); offsets / entries are indexed globally
+__global__ void k_msm_scatter(const uint32_t* keys, const uint32_t* ranks, const uint32_t* offsets, uint32_t n, size_t t0,
                               size_t total, uint32_t fold, uint32_t* entries) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
+    t += t0;
     uint32_t key = keys[t];
     if (key == KEY_NONE) return;
     uint32_t i = fold ? (uint32_t)t : (uint32_t)(t % n);
@@ -308,45 +314,6 @@ __global__ void __launch_bounds__(128, sizeof(F) > 32 ? B2_ACC_MINBLOCKS_G2 : B2
     else st16(task_sums + t, acc);
 }
 
-// G1 bucket accumulation in the carry-free 29-bit-limb field (fp29.cuh / ec29.cuh): identical task walk, the
-// accumulator lives in the 2^261 domain and is converted once when the task ends.  ~1.5x fewer FMA-pipe cycles per
-// addition than the 32-bit-limb kernel above; same buckets bit for bit once normalised (tests/test_gpu_msm.py).
-#ifndef B2_ACC29_MINBLOCKS
-#define B2_ACC29_MINBLOCKS 4
-#endif
-__global__ void __launch_bounds__(128, B2_ACC29_MINBLOCKS) k_msm_accumulate29_g1(const affine_t<Fq>* bases, const uint32_t* entries, const uint32_t* offsets,
-                                 const uint32_t* task_off, const uint32_t* task_bucket, const uint32_t* order,
-                                 uint32_t nbuckets, uint32_t task_len, uint32_t wave, xyzz_t<Fq>* buckets, xyzz_t<Fq>* task_sums) {
-    const uint32_t ntask = task_off[nbuckets];
-    const uint32_t nblk = (ntask + blockDim.x - 1) / blockDim.x;
-    if (blockIdx.x >= nblk) return;
-    uint32_t vb = blockIdx.x;
-    const uint32_t stride = nblk / wave;
-    if (stride > 1) {                      // same staggered block order as k_msm_accumulate
-        if (vb < wave) vb *= stride;
-        else {
-            uint32_t j = vb - wave;
-            vb = j < wave * (stride - 1) ? (j / (stride - 1)) * stride + j % (stride - 1) + 1 : wave * stride + (j - wave * (stride - 1));
-        }
-    }
-    uint32_t tid = vb * blockDim.x + threadIdx.x;
-    if (tid >= ntask) return;
-    uint32_t t = order[tid];
-    uint32_t g = task_bucket[t];
-    uint32_t t0 = task_off[g], nt = task_off[g + 1] - t0;
-    uint32_t lo = offsets[g] + (t - t0) * task_len, end = offsets[g + 1];
-    uint32_t hi = lo + task_len < end ? lo + task_len : end;
-    xyzz29_g1 acc = xyzz29_g1::identity();
-    for (uint32_t k = lo; k < hi; ++k) {
-        uint32_t e = entries[k];
-        affine_t<Fq> p = ld16(bases + (e & 0x7FFFFFFFu));
-        xyzz29_g1::madd(acc, p, (e >> 31) != 0);
-    }
-    xyzz_t<Fq> out = xyzz29_g1::to_xyzz(acc);
-    if (nt == 1) st16(buckets + g, out);
-    else st16(task_sums + t, out);
-}
-
 template <class F>
 __device__ __forceinline__ xyzz_t<F> add_sel(const xyzz_t<F>& a, const xyzz_t<F>& b) {
     if (sizeof(F) == 32) return xyzz_t<F>::add_inl(a, b);      // G1: inline (see k_msm_reduce_segments)
@@ -445,34 +412,49 @@ __global__ void __launch_bounds__(THREADS) k_msm_window_sum(const xyzz_t<F>* par
     if (threadIdx.x == 0) st16(wsum + blockIdx.x, sh[0]);
 }
 
-// 6. Horner over windows: one quad; the (up to 4) independent field products of each level of a point operation
-// are computed by the 4 lanes in the same instruction stream and exchanged through shared memory (quad_ops)
+// 6. Horner over the bucket sets, in the order the digit kernels number them (top window first).  One launch folds the
+// `nset` window sums of ONE window group into the running chain kept in `state` (first: the chain starts here; last: the
+// result goes to `out`), so the c doublings per window of group g run while the bucket kernel of group g + 1 occupies
+// the SMs.  One quad: the (up to 4) independent field products of each level of a point operation are computed by the
+// 4 lanes in the same instruction stream and exchanged through shared memory (quad_ops).  c = 0 (fixed-base tables):
+// a plain sum of the nset partial sums.
 template <class F>
-__global__ void __launch_bounds__(32) k_msm_combine(const xyzz_t<F>* wsum, uint32_t W, uint32_t c, xyzz_t<F>* out) {
+__global__ void __launch_bounds__(32) k_msm_horner(const xyzz_t<F>* wsum, uint32_t nset, uint32_t c, uint32_t first, uint32_t last,
+                                                   xyzz_t<F>* state, xyzz_t<F>* out) {
     typedef quad_ops<F, false> Q;
     __shared__ typename Q::xch_t xch;
     if (blockIdx.x != 0 || threadIdx.x >= 4) return;
-    xyzz_t<F> total = ld16(wsum + (W - 1));
-    for (int w = (int)W - 2; w >= 0; --w) {
-        for (uint32_t k = 0; k < c; ++k) total = Q::dbl(&xch, total);
-        total = Q::add(&xch, total, ld16(wsum + w));
+    xyzz_t<F> total;
+    uint32_t k = 0;
+    if (first) { total = ld16(wsum); k = 1; }
+    else total = ld16(state);
+    for (; k < nset; ++k) {
+        for (uint32_t j = 0; j < c; ++j) total = Q::dbl(&xch, total);
+        total = Q::add(&xch, total, ld16(wsum + k));
     }
-    if (threadIdx.x == 0) st16(out, total);
+    if (threadIdx.x == 0) st16(last ? out : state, total);
 }
 
-// GLV variant: quad 0 runs the Horner chain of windows [0, Wh), quad 1 that of [Wh, 2 Wh) in the same warp (half as
-// many sequential doublings); result = H0 + phi(H1), phi(X, Y, ZZ, ZZZ) = (beta X, Y, ZZ, ZZZ).
-__global__ void __launch_bounds__(32) k_msm_combine_glv(const xyzz_t<Fq>* wsum, uint32_t Wh, uint32_t c, xyzz_t<Fq>* out) {
+// GLV variant: quad 0 runs the chain of the |k1| windows (sets 2k), quad 1 that of the |k2| windows (sets 2k + 1) in
+// the same warp (half as many sequential doublings); result = H0 + phi(H1), phi(X, Y, ZZ, ZZZ) = (beta X, Y, ZZ, ZZZ).
+__global__ void __launch_bounds__(32) k_msm_horner_glv(const xyzz_t<Fq>* wsum, uint32_t nwin, uint32_t c, uint32_t first, uint32_t last,
+                                                       xyzz_t<Fq>* state, xyzz_t<Fq>* out) {
     typedef quad_ops<Fq, false> Q;
     __shared__ Q::xch_t xch[2];
     __shared__ xyzz_t<Fq> h1;
     if (blockIdx.x != 0 || threadIdx.x >= 8) return;
     const uint32_t half = threadIdx.x >> 2;
-    const xyzz_t<Fq>* ws = wsum + half * Wh;
-    xyzz_t<Fq> total = ld16(ws + (Wh - 1));
-    for (int w = (int)Wh - 2; w >= 0; --w) {
-        for (uint32_t k = 0; k < c; ++k) total = Q::dbl(&xch[half], total);
-        total = Q::add(&xch[half], total, ld16(ws + w));
+    xyzz_t<Fq> total;
+    uint32_t k = 0;
+    if (first) { total = ld16(wsum + half); k = 1; }
+    else total = ld16(state + half);
+    for (; k < nwin; ++k) {
+        for (uint32_t j = 0; j < c; ++j) total = Q::dbl(&xch[half], total);
+        total = Q::add(&xch[half], total, ld16(wsum + 2 * k + half));
+    }
+    if (!last) {
+        if ((threadIdx.x & 3) == 0) st16(state + half, total);
+        return;
     }
     if (threadIdx.x == 4) h1 = total;
     __syncwarp(0xFFu);
@@ -533,16 +515,68 @@ static int exclusive_scan(b200zk_ctx* ctx, cudaStream_t st, const uint32_t* in, 
     return check_launch(ctx, "scan");
 }
 
+// event `idx` of MSM channel `ch` (common.cuh), created on first use; only called under the owning slot's mutex
+static cudaEvent_t msm_event(b200zk_ctx* ctx, int ch, size_t idx) {
+    std::vector<cudaEvent_t>& v = ctx->msm_events[ch];
+    while (v.size() <= idx) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        v.push_back(e);
+    }
+    return v[idx];
+}
+
+// Streams of one MSM.  `seq`: digit / sort phases and, per window group, merge + bucket reduction + Horner step;
+// `acc`: the bucket kernels; `result`: the stream the caller orders the result on.  A plain call runs the bucket
+// kernels on the caller's stream and everything else on the channel's high-priority side stream; a prove lane brings
+// its own pair (lane.st is `seq` and `result`).
+struct MsmStreams {
+    cudaStream_t seq, acc;
+    bool result_on_seq;
+    int channel;
+};
+
+// The window-group pipeline (one MSM, no host round trips):
+//   seq : digits, scan | prep(0) | prep(1) .. prep(G-1) | wait A0: tail(0) | wait A1: tail(1) | ...
+//   acc :                 wait P0: accumulate(0) -> A0 | wait P1: accumulate(1) -> A1 | ...
+// prep(g) = task tables + scatter of group g's bucket sets, tail(g) = merge + bucket reduction + window sums + Horner
+// step.  Groups hold consecutive bucket sets in Horner order (top windows first), so tail(g) -- a chain of dependent
+// point operations that used to follow the bucket kernel (1.0 of 4.0 ms at 2^20) -- overlaps accumulate(g + 1); only
+// the last group's tail is exposed.  `seq` has the higher stream priority: its short kernels get the SM slots that
+// the running bucket kernel frees, instead of queueing behind it.
 template <class F>
-static int msm_dev_impl(b200zk_ctx* ctx, cudaStream_t st, DevBuf& ws_buf, const void* d_bases, const void* d_scalars, size_t n,
+static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, const void* d_bases, const void* d_scalars, size_t n,
                         void* d_out, const char* acc_name, cudaEvent_t bases_ready, cudaEvent_t scalars_ready = nullptr,
-                        unsigned tab_c = 0, const MsmLane* lane = nullptr, unsigned c_force = 0) {
+                        unsigned tab_c = 0, unsigned c_force = 0) {
+    const cudaStream_t st = ms.seq, ast = ms.acc;
+    const int ch = ms.channel;
+    size_t nev = 0;
+    auto next_event = [&]() { return msm_event(ctx, ch, nev++); };
+    // inputs were produced in `result`-stream order
+    if (!ms.result_on_seq) {
+        cudaEvent_t e = next_event();
+        if (!e) return set_error(ctx, B200ZK_ERR_CUDA, "cudaEventCreate failed");
+        B2_CUDA_OK(ctx, cudaEventRecord(e, ast));
+        B2_CUDA_OK(ctx, cudaStreamWaitEvent(st, e, 0));
+    }
+    auto finish = [&]() -> int {          // the result (written on seq) becomes visible in result-stream order
+        if (!ms.result_on_seq) {
+            cudaEvent_t e = next_event();
+            if (!e) return set_error(ctx, B200ZK_ERR_CUDA, "cudaEventCreate failed");
+            B2_CUDA_OK(ctx, cudaEventRecord(e, st));
+            B2_CUDA_OK(ctx, cudaStreamWaitEvent(ast, e, 0));
+        }
+        return B200ZK_OK;
+    };
     if (scalars_ready) B2_CUDA_OK(ctx, cudaStreamWaitEvent(st, scalars_ready, 0));
     xyzz_t<F>* out = reinterpret_cast<xyzz_t<F>*>(d_out);
     if (n == 0) {
-        LaunchScope ls(ctx, st, "msm_small");
-        k_set_identity<F><<<1, 32, 0, st>>>(out);
-        return check_launch(ctx, "k_set_identity");
+        {
+            LaunchScope ls(ctx, st, "msm_small");
+            k_set_identity<F><<<1, 32, 0, st>>>(out);
+        }
+        B2_TRY(check_launch(ctx, "k_set_identity"));
+        return finish();
     }
     if (n >= (1ull << 31)) return set_error(ctx, B200ZK_ERR_ARG, "MSM length must be < 2^31");
     // tab_c != 0: d_bases is a fixed-base table of msm_table_windows(tab_c) x n points (section 7); all digit windows
@@ -568,14 +602,22 @@ static int msm_dev_impl(b200zk_ctx* ctx, cudaStream_t st, DevBuf& ws_buf, const 
     const uint32_t wsplit = (fold && nseg >= 16 * 256) ? 16 : 1;
     const size_t total = (size_t)W * n;
 
+    // window groups: `spg` consecutive bucket sets each (GLV: whole windows, i.e. both halves).  Small inputs are
+    // launch-latency bound and stay in one group.
+    unsigned ngroups = 1;
+    if (!fold && n >= (1u << 17)) {
+        static const int g_env = getenv("B200ZK_MSM_GROUPS") ? atoi(getenv("B200ZK_MSM_GROUPS")) : 0;
+        const unsigned units = glv ? Wh : W;                 // windows
+        unsigned want = g_env > 0 ? (unsigned)g_env : 4;
+        if (want > units) want = units;
+        ngroups = want;
+    }
+    const unsigned unit_sets = glv ? 2 : 1;
+    const unsigned units = (fold ? 1 : (glv ? Wh : W));
+    auto group_first_unit = [&](unsigned g) { return (unsigned)(((uint64_t)units * g) / ngroups); };   // balanced split
+
     // workspace carve-up (256-byte aligned)
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    size_t o_keys = 0;
-    size_t o_ranks = o_keys + al(total * 4);
-    size_t o_entries = o_ranks + al(total * 4);
-    size_t o_counts = o_entries + al(total * 4);
-    size_t o_offsets = o_counts + al(((size_t)nb + 1) * 4);
-    size_t o_sums = o_offsets + al(((size_t)nb + 1) * 4);
     // task length: 128 unless the average bucket is already that long (n >> 2^c: every bucket would be cut in two);
     // then the next power of two above 3x the average -- only outliers are split -- as long as that leaves enough
     // tasks (>= 2^19) to fill the machine
@@ -583,20 +625,23 @@ static int msm_dev_impl(b200zk_ctx* ctx, cudaStream_t st, DevBuf& ws_buf, const 
     while (task_len < MAX_TASK_LEN && (uint64_t)task_len * nb < 3 * (uint64_t)total &&
            total / (2 * task_len) + nb >= (1u << 19))
         task_len *= 2;
-    const size_t max_tasks = total / task_len + nb + 1;
-    size_t o_ntasks = o_sums + al(((size_t)nb / SCAN_TILE + 2) * 4);
-    size_t o_taskoff = o_ntasks + al(((size_t)nb + 1) * 4);
-    size_t o_taskbucket = o_taskoff + al(((size_t)nb + 1) * 4);
-    size_t o_multi = o_taskbucket + al(max_tasks * 4);
-    size_t o_hist = o_multi + al((total / task_len + 4) * 4);
-    size_t o_rank = o_hist + al((MAX_TASK_LEN + 1) * 4);
-    size_t o_order = o_rank + al(max_tasks * 4);
-    size_t o_tasksums = o_order + al(max_tasks * 4);
-    size_t o_buckets = o_tasksums + al(max_tasks * sizeof(xyzz_t<F>));
-    size_t o_partials = o_buckets + al((size_t)nb * sizeof(xyzz_t<F>));
-    size_t o_wsum = o_partials + al((size_t)WB * nseg * sizeof(xyzz_t<F>));
-    size_t ws_bytes = o_wsum + al((size_t)WB * wsplit * sizeof(xyzz_t<F>));
-    B2_CUDA_OK(ctx, ws_buf.reserve(ws_bytes));
+    const size_t max_tasks = total / task_len + nb + ngroups;                 // all groups together
+    size_t o = 0;
+    auto carve = [&](size_t bytes) { size_t r = o; o += al(bytes); return r; };
+    const size_t o_keys = carve(total * 4), o_ranks = carve(total * 4), o_entries = carve(total * 4);
+    const size_t o_counts = carve(((size_t)nb + 1) * 4), o_offsets = carve(((size_t)nb + 1) * 4);
+    const size_t o_sums = carve(((size_t)nb / SCAN_TILE + 2) * 4);
+    const size_t o_ntasks = carve(((size_t)nb + ngroups) * 4), o_taskoff = carve(((size_t)nb + ngroups) * 4);
+    const size_t o_taskbucket = carve(max_tasks * 4);
+    const size_t o_multi = carve((total / task_len + 4 * ngroups + 4) * 4);
+    const size_t o_hist = carve((size_t)ngroups * (MAX_TASK_LEN + 1) * 4);
+    const size_t o_rank = carve(max_tasks * 4), o_order = carve(max_tasks * 4);
+    const size_t o_tasksums = carve(max_tasks * sizeof(xyzz_t<F>));
+    const size_t o_buckets = carve((size_t)nb * sizeof(xyzz_t<F>));
+    const size_t o_partials = carve((size_t)WB * nseg * sizeof(xyzz_t<F>));
+    const size_t o_wsum = carve((size_t)WB * wsplit * sizeof(xyzz_t<F>));
+    const size_t o_state = carve(2 * sizeof(xyzz_t<F>));
+    B2_CUDA_OK(ctx, ws_buf.reserve(o));
     char* ws = reinterpret_cast<char*>(ws_buf.p);
     uint32_t* keys = reinterpret_cast<uint32_t*>(ws + o_keys);
     uint32_t* ranks = reinterpret_cast<uint32_t*>(ws + o_ranks);
@@ -604,18 +649,18 @@ static int msm_dev_impl(b200zk_ctx* ctx, cudaStream_t st, DevBuf& ws_buf, const 
     uint32_t* counts = reinterpret_cast<uint32_t*>(ws + o_counts);
     uint32_t* offsets = reinterpret_cast<uint32_t*>(ws + o_offsets);
     uint32_t* sums = reinterpret_cast<uint32_t*>(ws + o_sums);
-    uint32_t* ntasks = reinterpret_cast<uint32_t*>(ws + o_ntasks);
-    uint32_t* task_off = reinterpret_cast<uint32_t*>(ws + o_taskoff);
-    uint32_t* task_bucket = reinterpret_cast<uint32_t*>(ws + o_taskbucket);
-    uint32_t* multi = reinterpret_cast<uint32_t*>(ws + o_multi);       // [0], [1] = big / small counts, [2..] = list
-    const uint32_t list_cap = (uint32_t)(total / task_len + 1);
-    uint32_t* hist = reinterpret_cast<uint32_t*>(ws + o_hist);
-    uint32_t* task_rank = reinterpret_cast<uint32_t*>(ws + o_rank);
-    uint32_t* order = reinterpret_cast<uint32_t*>(ws + o_order);
-    xyzz_t<F>* task_sums = reinterpret_cast<xyzz_t<F>*>(ws + o_tasksums);
+    uint32_t* ntasks_all = reinterpret_cast<uint32_t*>(ws + o_ntasks);
+    uint32_t* task_off_all = reinterpret_cast<uint32_t*>(ws + o_taskoff);
+    uint32_t* task_bucket_all = reinterpret_cast<uint32_t*>(ws + o_taskbucket);
+    uint32_t* multi_all = reinterpret_cast<uint32_t*>(ws + o_multi);
+    uint32_t* hist_all = reinterpret_cast<uint32_t*>(ws + o_hist);
+    uint32_t* task_rank_all = reinterpret_cast<uint32_t*>(ws + o_rank);
+    uint32_t* order_all = reinterpret_cast<uint32_t*>(ws + o_order);
+    xyzz_t<F>* task_sums_all = reinterpret_cast<xyzz_t<F>*>(ws + o_tasksums);
     xyzz_t<F>* buckets = reinterpret_cast<xyzz_t<F>*>(ws + o_buckets);
     xyzz_t<F>* partials = reinterpret_cast<xyzz_t<F>*>(ws + o_partials);
     xyzz_t<F>* wsum = reinterpret_cast<xyzz_t<F>*>(ws + o_wsum);
+    xyzz_t<F>* hstate = reinterpret_cast<xyzz_t<F>*>(ws + o_state);
 
     B2_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, ((size_t)nb + 1) * 4, st));
     {
@@ -627,41 +672,82 @@ static int msm_dev_impl(b200zk_ctx* ctx, cudaStream_t st, DevBuf& ws_buf, const 
     }
     B2_TRY(check_launch(ctx, "k_msm_digits"));
     B2_TRY(exclusive_scan(ctx, st, counts, offsets, sums, nb + 1));
-    {
-        LaunchScope ls(ctx, st, "msm_tasks");
-        k_msm_task_counts<<<(nb + 1 + 255) / 256, 256, 0, st>>>(offsets, nb, task_len, ntasks);
-    }
-    B2_TRY(check_launch(ctx, "k_msm_task_counts"));
-    B2_TRY(exclusive_scan(ctx, st, ntasks, task_off, sums, nb + 1));
-    B2_CUDA_OK(ctx, cudaMemsetAsync(multi, 0, 8, st));
+    B2_CUDA_OK(ctx, cudaMemsetAsync(multi_all, 0, (size_t)ngroups * 8, st));          // [2 g], [2 g + 1] = big / small counts
+    B2_CUDA_OK(ctx, cudaMemsetAsync(hist_all, 0, (size_t)ngroups * (MAX_TASK_LEN + 1) * 4, st));
     B2_CUDA_OK(ctx, cudaMemsetAsync(buckets, 0, (size_t)nb * sizeof(xyzz_t<F>), st));   // all-zero XYZZ = identity
+
+    // per-group views of the task tables
+    struct Group {
+        uint32_t set0, nsets, b0, nbk;          // bucket sets [set0, set0 + nsets), buckets [b0, b0 + nbk)
+        size_t task_cap, task_base;             // task arrays: [task_base, task_base + task_cap)
+        uint32_t list_cap; size_t list_base;    // multi-task bucket list
+        cudaEvent_t prepped, accumulated;
+    };
+    std::vector<Group> groups(ngroups);
     {
-        LaunchScope ls(ctx, st, "msm_tasks");
-        k_msm_fill_tasks<<<(nb + 255) / 256, 256, 0, st>>>(task_off, nb, task_bucket, multi + 2, list_cap, multi);
+        size_t tb = 0, lb = 2 * (size_t)ngroups;
+        for (unsigned g = 0; g < ngroups; ++g) {
+            Group& G = groups[g];
+            const unsigned u0 = group_first_unit(g), u1 = group_first_unit(g + 1);
+            G.set0 = u0 * unit_sets; G.nsets = (u1 - u0) * unit_sets;
+            G.b0 = G.set0 * B; G.nbk = G.nsets * B;
+            const size_t gtotal = fold ? total : (size_t)G.nsets * n;
+            G.task_cap = gtotal / task_len + G.nbk + 1;
+            G.task_base = tb; tb += G.task_cap;
+            G.list_cap = (uint32_t)(gtotal / task_len + 1);
+            G.list_base = lb; lb += G.list_cap;
+            G.prepped = next_event(); G.accumulated = next_event();
+            if (!G.prepped || !G.accumulated) return set_error(ctx, B200ZK_ERR_CUDA, "cudaEventCreate failed");
+        }
     }
-    B2_TRY(check_launch(ctx, "k_msm_fill_tasks"));
-    B2_CUDA_OK(ctx, cudaMemsetAsync(hist, 0, (MAX_TASK_LEN + 1) * 4, st));
-    {
-        LaunchScope ls(ctx, st, "msm_tasks");
-        k_msm_task_hist<<<(unsigned)((max_tasks + 255) / 256), 256, 0, st>>>(offsets, task_off, task_bucket, nb, task_len, hist, task_rank);
+
+    // ---- prep(g): task tables (counting sort of the <= task_len-entry tasks by length) + scatter, on seq ----------------
+    for (unsigned g = 0; g < ngroups; ++g) {
+        const Group& G = groups[g];
+        uint32_t* ntasks = ntasks_all + G.b0 + g;               // nbk + 1 entries per group
+        uint32_t* task_off = task_off_all + G.b0 + g;
+        uint32_t* task_bucket = task_bucket_all + G.task_base;
+        uint32_t* task_rank = task_rank_all + G.task_base;
+        uint32_t* order = order_all + G.task_base;
+        uint32_t* hist = hist_all + (size_t)g * (MAX_TASK_LEN + 1);
+        {
+            LaunchScope ls(ctx, st, "msm_tasks");
+            k_msm_task_counts<<<(G.nbk + 1 + 255) / 256, 256, 0, st>>>(offsets + G.b0, G.nbk, task_len, ntasks);
+        }
+        B2_TRY(check_launch(ctx, "k_msm_task_counts"));
+        B2_TRY(exclusive_scan(ctx, st, ntasks, task_off, sums, G.nbk + 1));
+        {
+            LaunchScope ls(ctx, st, "msm_tasks");
+            k_msm_fill_tasks<<<(G.nbk + 255) / 256, 256, 0, st>>>(task_off, G.nbk, task_bucket, multi_all + G.list_base, G.list_cap,
+                                                                  multi_all + 2 * g);
+        }
+        B2_TRY(check_launch(ctx, "k_msm_fill_tasks"));
+        {
+            LaunchScope ls(ctx, st, "msm_tasks");
+            k_msm_task_hist<<<(unsigned)((G.task_cap + 255) / 256), 256, 0, st>>>(offsets + G.b0, task_off, task_bucket, G.nbk, task_len, hist, task_rank);
+        }
+        {
+            LaunchScope ls(ctx, st, "msm_tasks");
+            k_msm_task_hist_scan<<<1, 1, 0, st>>>(hist, task_len);
+        }
+        {
+            LaunchScope ls(ctx, st, "msm_tasks");
+            k_msm_task_order<<<(unsigned)((G.task_cap + 255) / 256), 256, 0, st>>>(offsets + G.b0, task_off, task_bucket, G.nbk, task_len, hist, task_rank, order);
+        }
+        B2_TRY(check_launch(ctx, "k_msm_task_order"));
+        {
+            const size_t t0 = fold ? 0 : (size_t)G.set0 * n, cnt = fold ? total : (size_t)G.nsets * n;
+            LaunchScope ls(ctx, st, "msm_scatter");
+            k_msm_scatter<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(keys, ranks, offsets, (uint32_t)n, t0, cnt, fold ? 1u : 0u, entries);
+        }
+        B2_TRY(check_launch(ctx, "k_msm_scatter"));
+        B2_CUDA_OK(ctx, cudaEventRecord(G.prepped, st));
     }
-    {
-        LaunchScope ls(ctx, st, "msm_tasks");
-        k_msm_task_hist_scan<<<1, 1, 0, st>>>(hist, task_len);
-    }
-    {
-        LaunchScope ls(ctx, st, "msm_tasks");
-        k_msm_task_order<<<(unsigned)((max_tasks + 255) / 256), 256, 0, st>>>(offsets, task_off, task_bucket, nb, task_len, hist, task_rank, order);
-    }
-    B2_TRY(check_launch(ctx, "k_msm_task_order"));
-    {
-        LaunchScope ls(ctx, st, "msm_scatter");
-        k_msm_scatter<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(keys, ranks, offsets, (uint32_t)n, total, fold ? 1u : 0u, entries);
-    }
-    B2_TRY(check_launch(ctx, "k_msm_scatter"));
+
+    // ---- accumulate(g) on acc ---------------------------------------------------------------------------------------------
     // the digit / sort phases above only read the scalars: a caller staging host buffers lets the H2D copy of
     // the (2-4x larger) base array overlap them and signals its arrival here
-    if (bases_ready) B2_CUDA_OK(ctx, cudaStreamWaitEvent(st, bases_ready, 0));
+    if (bases_ready) B2_CUDA_OK(ctx, cudaStreamWaitEvent(ast, bases_ready, 0));
     bool l2_window = false;
     if (ctx->l2_persist_max && ctx->l2_window_max) {
         // every base point is gathered once per window (W times per launch): pin the array in L2
@@ -674,81 +760,85 @@ static int msm_dev_impl(b200zk_ctx* ctx, cudaStream_t st, DevBuf& ws_buf, const 
         attr.accessPolicyWindow.hitRatio = ratio > 1.0 ? 1.0f : (float)ratio;
         attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        l2_window = cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
+        l2_window = cudaStreamSetAttribute(ast, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
         cudaGetLastError();
     }
-    {
-        // lane (prove_dev): the bucket kernel goes to a lower-priority stream than the rest of this MSM, so that the
-        // short digit / sort / reduction kernels of concurrent MSMs are dispatched between its blocks instead of
-        // queueing behind whole bucket kernels of other streams
-        cudaStream_t ast = lane ? lane->acc_st : st;
-        if (lane) {
-            B2_CUDA_OK(ctx, cudaEventRecord(lane->ev_sorted, st));
-            B2_CUDA_OK(ctx, cudaStreamWaitEvent(ast, lane->ev_sorted, 0));
-        }
+    for (unsigned g = 0; g < ngroups; ++g) {
+        const Group& G = groups[g];
+        B2_CUDA_OK(ctx, cudaStreamWaitEvent(ast, G.prepped, 0));
         {
             LaunchScope ls(ctx, ast, acc_name);
-            static const bool acc29 = !(getenv("B200ZK_ACC29") && getenv("B200ZK_ACC29")[0] == '0');
-            if (sizeof(F) == 32 && acc29)
-                k_msm_accumulate29_g1<<<(unsigned)((max_tasks + 127) / 128), 128, 0, ast>>>(
-                    reinterpret_cast<const affine_t<Fq>*>(d_bases), entries, offsets, task_off, task_bucket, order, nb, task_len,
-                    (uint32_t)ctx->sm_count * B2_ACC29_MINBLOCKS, reinterpret_cast<xyzz_t<Fq>*>(buckets), reinterpret_cast<xyzz_t<Fq>*>(task_sums));
-            else
-                k_msm_accumulate<F><<<(unsigned)((max_tasks + 127) / 128), 128, 0, ast>>>(
-                    reinterpret_cast<const affine_t<F>*>(d_bases), entries, offsets, task_off, task_bucket, order, nb, task_len,
-                    (uint32_t)ctx->sm_count * (sizeof(F) > 32 ? B2_ACC_MINBLOCKS_G2 : B2_ACC_MINBLOCKS), buckets, task_sums);
+            k_msm_accumulate<F><<<(unsigned)((G.task_cap + 127) / 128), 128, 0, ast>>>(
+                reinterpret_cast<const affine_t<F>*>(d_bases), entries, offsets + G.b0, task_off_all + G.b0 + g, task_bucket_all + G.task_base,
+                order_all + G.task_base, G.nbk, task_len, (uint32_t)ctx->sm_count * (sizeof(F) > 32 ? B2_ACC_MINBLOCKS_G2 : B2_ACC_MINBLOCKS),
+                buckets + G.b0, task_sums_all + G.task_base);
         }
-        if (lane) {
-            B2_CUDA_OK(ctx, cudaEventRecord(lane->ev_acc, ast));
-            B2_CUDA_OK(ctx, cudaStreamWaitEvent(st, lane->ev_acc, 0));
-        }
+        B2_TRY(check_launch(ctx, "k_msm_accumulate"));
+        B2_CUDA_OK(ctx, cudaEventRecord(G.accumulated, ast));
     }
-    B2_TRY(check_launch(ctx, "k_msm_accumulate"));
     if (l2_window) {
         cudaStreamAttrValue attr;
         memset(&attr, 0, sizeof(attr));
         attr.accessPolicyWindow.num_bytes = 0;
-        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaStreamSetAttribute(ast, cudaStreamAttributeAccessPolicyWindow, &attr);
         cudaGetLastError();
     }
-    {
-        LaunchScope ls(ctx, st, "msm_merge");
-        k_msm_merge_tasks<F><<<2 * ctx->sm_count, 128, 0, st>>>(multi + 2, multi, task_off, task_sums, buckets);
+
+    // ---- tail(g) on seq: merge, bucket reduction, window sums, Horner step ----------------------------------------------
+    for (unsigned g = 0; g < ngroups; ++g) {
+        const Group& G = groups[g];
+        B2_CUDA_OK(ctx, cudaStreamWaitEvent(st, G.accumulated, 0));
+        uint32_t* task_off = task_off_all + G.b0 + g;
+        {
+            LaunchScope ls(ctx, st, "msm_merge");
+            k_msm_merge_tasks<F><<<2 * ctx->sm_count, 128, 0, st>>>(multi_all + G.list_base, multi_all + 2 * g, task_off,
+                                                                   task_sums_all + G.task_base, buckets + G.b0);
+        }
+        {
+            LaunchScope ls(ctx, st, "msm_merge");
+            k_msm_merge_small<F><<<4 * ctx->sm_count, 128, 0, st>>>(multi_all + G.list_base, G.list_cap, multi_all + 2 * g + 1, task_off,
+                                                                   task_sums_all + G.task_base, buckets + G.b0);
+        }
+        B2_TRY(check_launch(ctx, "k_msm_merge_tasks"));
+        {
+            LaunchScope ls(ctx, st, "msm_reduce");
+            k_msm_reduce_segments<F><<<(G.nsets * nseg + 127) / 128, 128, 0, st>>>(buckets + G.b0, G.nsets, B, seg_len,
+                                                                                  partials + (size_t)G.set0 * nseg);
+        }
+        B2_TRY(check_launch(ctx, "k_msm_reduce_segments"));
+        {
+            LaunchScope ls(ctx, st, "msm_window_sum");
+            constexpr int T = sizeof(F) > 32 ? 128 : 256;
+            // fold: the single bucket set's partials are summed by `wsplit` blocks, then added up by the Horner kernel
+            // with zero doublings per step
+            k_msm_window_sum<F, T><<<G.nsets * wsplit, T, 0, st>>>(partials + (size_t)G.set0 * nseg, nseg / wsplit, wsum + (size_t)G.set0 * wsplit);
+        }
+        B2_TRY(check_launch(ctx, "k_msm_window_sum"));
+        {
+            LaunchScope ls(ctx, st, "msm_combine");
+            const uint32_t first = g == 0, last = g + 1 == ngroups;
+            if (glv) k_msm_horner_glv<<<1, 32, 0, st>>>(reinterpret_cast<const xyzz_t<Fq>*>(wsum) + G.set0, G.nsets / 2, c, first, last,
+                                                        reinterpret_cast<xyzz_t<Fq>*>(hstate), reinterpret_cast<xyzz_t<Fq>*>(out));
+            else k_msm_horner<F><<<1, 32, 0, st>>>(wsum + (size_t)G.set0 * wsplit, G.nsets * wsplit, fold ? 0u : c, first, last, hstate, out);
+        }
+        B2_TRY(check_launch(ctx, "k_msm_horner"));
     }
-    {
-        LaunchScope ls(ctx, st, "msm_merge");
-        k_msm_merge_small<F><<<4 * ctx->sm_count, 128, 0, st>>>(multi + 2, list_cap, multi + 1, task_off, task_sums, buckets);
-    }
-    B2_TRY(check_launch(ctx, "k_msm_merge_tasks"));
-    {
-        LaunchScope ls(ctx, st, "msm_reduce");
-        k_msm_reduce_segments<F><<<(WB * nseg + 127) / 128, 128, 0, st>>>(buckets, WB, B, seg_len, partials);
-    }
-    B2_TRY(check_launch(ctx, "k_msm_reduce_segments"));
-    {
-        LaunchScope ls(ctx, st, "msm_window_sum");
-        constexpr int T = sizeof(F) > 32 ? 128 : 256;
-        // fold: the single bucket set's partials are summed by FOLD_SPLIT blocks, then added up by the combine
-        // kernel with zero doublings per step
-        k_msm_window_sum<F, T><<<WB * wsplit, T, 0, st>>>(partials, nseg / wsplit, wsum);
-    }
-    B2_TRY(check_launch(ctx, "k_msm_window_sum"));
-    {
-        LaunchScope ls(ctx, st, "msm_combine");
-        if (glv) k_msm_combine_glv<<<1, 32, 0, st>>>(reinterpret_cast<const xyzz_t<Fq>*>(wsum), Wh, c, reinterpret_cast<xyzz_t<Fq>*>(out));
-        else k_msm_combine<F><<<1, 32, 0, st>>>(wsum, WB * wsplit, fold ? 0u : c, out);
-    }
-    return check_launch(ctx, "k_msm_combine");
+    return finish();
+}
+
+static MsmStreams slot_streams(b200zk_ctx* ctx, Slot& sl, int aux) {
+    const int ch = 2 * (int)(&sl - ctx->slots) + (aux ? 1 : 0);
+    return MsmStreams{ctx->msm_side[ch], aux ? sl.aux_stream : sl.stream, false, ch};
 }
 
 int msm_g1_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n, void* d_out,
                cudaEvent_t bases_ready, int aux) {
-    return msm_dev_impl<Fq>(ctx, aux ? sl.aux_stream : sl.stream, aux ? sl.ws_msm_aux : sl.ws_msm, d_bases, d_scalars, n, d_out,
+    return msm_dev_impl<Fq>(ctx, slot_streams(ctx, sl, aux), aux ? sl.ws_msm_aux : sl.ws_msm, d_bases, d_scalars, n, d_out,
                             "msm_accumulate_g1", bases_ready);
 }
 int msm_g2_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n, void* d_out,
                cudaEvent_t bases_ready, int aux) {
-    return msm_dev_impl<Fq2>(ctx, aux ? sl.aux_stream : sl.stream, aux ? sl.ws_msm_aux : sl.ws_msm, d_bases, d_scalars, n, d_out,
+    return msm_dev_impl<Fq2>(ctx, slot_streams(ctx, sl, aux), aux ? sl.ws_msm_aux : sl.ws_msm, d_bases, d_scalars, n, d_out,
                              "msm_accumulate_g2", bases_ready);
 }
 
@@ -811,7 +901,7 @@ int msm_table_build_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_bases, 
 int msm_table_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_table, const void* d_scalars, size_t n, unsigned c,
                   void* d_out, int aux) {
     if (c < 2 || c > 24) return set_error(ctx, B200ZK_ERR_ARG, "table window must be in [2, 24]");
-    cudaStream_t st = aux ? sl.aux_stream : sl.stream;
+    const MsmStreams st = slot_streams(ctx, sl, aux);
     DevBuf& ws = aux ? sl.ws_msm_aux : sl.ws_msm;
     return g2 ? msm_dev_impl<Fq2>(ctx, st, ws, d_table, d_scalars, n, d_out, "msm_accumulate_g2", nullptr, nullptr, c)
               : msm_dev_impl<Fq>(ctx, st, ws, d_table, d_scalars, n, d_out, "msm_accumulate_g1", nullptr, nullptr, c);
@@ -819,8 +909,9 @@ int msm_table_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_table, const 
 
 int msm_lane_dev(b200zk_ctx* ctx, const MsmLane& lane, int g2, unsigned tab_c, const void* d_bases, const void* d_scalars,
                  size_t n, void* d_out) {
-    return g2 ? msm_dev_impl<Fq2>(ctx, lane.st, *lane.ws, d_bases, d_scalars, n, d_out, "msm_accumulate_g2", nullptr, nullptr, tab_c, &lane)
-              : msm_dev_impl<Fq>(ctx, lane.st, *lane.ws, d_bases, d_scalars, n, d_out, "msm_accumulate_g1", nullptr, nullptr, tab_c, &lane);
+    const MsmStreams st{lane.st, lane.acc_st, true, lane.channel};
+    return g2 ? msm_dev_impl<Fq2>(ctx, st, *lane.ws, d_bases, d_scalars, n, d_out, "msm_accumulate_g2", nullptr, nullptr, tab_c)
+              : msm_dev_impl<Fq>(ctx, st, *lane.ws, d_bases, d_scalars, n, d_out, "msm_accumulate_g1", nullptr, nullptr, tab_c);
 }
 
 // Host-staged G1 MSM in two halves on two streams: the H2D copy of the second half and the latency-bound tail of the
@@ -835,9 +926,9 @@ int msm_g1_two_halves_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const 
     // both halves use the window of the whole length: with GLV, 2^19 points at c = 15 cost 18 bucket additions per scalar
     // against 16 at c = 16, and the larger bucket reduction overlaps the other half anyway (e2e 5.44 -> 5.08 ms at 2^20)
     const unsigned c = choose_window(n1 + n2);
-    B2_TRY(msm_dev_impl<Fq>(ctx, sl.stream, sl.ws_msm, b, s, n1, out, "msm_accumulate_g1", ev[1], ev[0], 0, nullptr, c));
-    B2_TRY(msm_dev_impl<Fq>(ctx, sl.aux_stream, sl.ws_msm_aux, b + n1 * 64, s + n1 * 32, n2, out + 128, "msm_accumulate_g1", ev[3], ev[2],
-                            0, nullptr, c));
+    B2_TRY(msm_dev_impl<Fq>(ctx, slot_streams(ctx, sl, 0), sl.ws_msm, b, s, n1, out, "msm_accumulate_g1", ev[1], ev[0], 0, c));
+    B2_TRY(msm_dev_impl<Fq>(ctx, slot_streams(ctx, sl, 1), sl.ws_msm_aux, b + n1 * 64, s + n1 * 32, n2, out + 128, "msm_accumulate_g1", ev[3], ev[2],
+                            0, c));
     B2_CUDA_OK(ctx, cudaEventRecord(sl.aux_done, sl.aux_stream));
     B2_CUDA_OK(ctx, cudaStreamWaitEvent(sl.stream, sl.aux_done, 0));
     return B200ZK_OK;

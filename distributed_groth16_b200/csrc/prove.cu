@@ -213,7 +213,7 @@ int prove_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const Fr* d_z, const Fr* d_a
                                        // its longer dependency chains are hidden by the concurrent MSMs (-0.3 ms at 2^20)
     if (use_lanes) {
         auto msm = [&](int lane_id, DevBuf& ws, int k, int g2, const void* query, const Fr* scalars, size_t n, void* out) -> int {
-            MsmLane lane{ctx->lane_main[lane_id], &ws, ctx->lane_acc[lane_id], ctx->lane_ev[lane_id][0], ctx->lane_ev[lane_id][1]};
+            MsmLane lane{ctx->lane_main[lane_id], &ws, ctx->lane_acc[lane_id], 6 + lane_id};
             return msm_lane_dev(ctx, lane, g2, pk->tab_c[k], pk->tab_c[k] ? pk->tab[k] : query, scalars, n, out);
         };
         cudaStreamWaitEvent(ctx->hi_stream, ev_in, 0);

@@ -11,7 +11,7 @@
 // finished bucket leaves as an ordinary xyzz_t<Fq> (4 products with the constant 2^256), so nothing outside the
 // bucket kernel sees this representation.
 #pragma once
-#include "ec.cuh"
+#include "../../distributed_groth16_b200/csrc/ec.cuh"
 #include "fp29.cuh"
 
 namespace b200zk {

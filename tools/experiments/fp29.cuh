@@ -1,4 +1,10 @@
-// fp29.cuh -- carry-free 9 x 29-bit-limb Montgomery arithmetic for the hot loops (BN254 Fq and Fr) on sm_100a.
+// fp29.cuh -- EXPERIMENT (not part of the product library): carry-free 9 x 29-bit-limb Montgomery arithmetic.
+//
+// Outcome on B200 (profiles/r2_microbench.txt): correct (bit-identical to fp.cuh through the domain changes, host +
+// device) but SLOWER: 52 G products/s against 66-69 G/s for the 8 x 32-bit-limb product of fp.cuh.  The premise below
+// was wrong: round 1's "IMAD.WIDE.U32 without carry = 60 lanes/clk" probe had its multiplies hoisted out of the loop
+// by ptxas (the loop measured IADD3).  Every 32x32->64 multiply-add issues at 32 lanes/clk/SM whatever its addend,
+// so 171 of them (9 x 9 x 2 + 9) lose to 128 + 16.  Kept for the record and for tools/microbench.cu.
 //
 // Why a second representation.  tools/microbench.cu on B200 (profiles/r1_microbench_pipes.txt): a wide multiply-add
 // that consumes or produces a carry (IMAD.WIDE.U32.X, what a saturated 8 x 32-bit-limb product is made of, fp.cuh)
@@ -20,7 +26,7 @@
 // canonical 8 x u32 Montgomery words.  Plain C++ on purpose (nvcc turns `t += (u64)a * b` into IMAD.WIDE.U32 with a
 // 64-bit addend), so the identical code is unit-tested on the host (tests/host/fp_host_test.cpp).
 #pragma once
-#include "fp.cuh"
+#include "../../distributed_groth16_b200/csrc/fp.cuh"
 
 namespace b200zk {
 

@@ -2,7 +2,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench tools/microbench.cu
 #include <cstdio>
 #include <cuda_runtime.h>
-#include "../distributed_groth16_b200/csrc/ec29.cuh"
+#include "experiments/ec29.cuh"
 using namespace b200zk;
 
 #define ITERS 2000
@@ -35,6 +35,32 @@ __global__ void k_imad_wide(uint64_t* out, uint32_t a, uint32_t b) {
         for (int i = 0; i < 8; ++i) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(r[i]) : "r"(a + i), "r"(b));
     }
     uint64_t s = 0; for (int i = 0; i < 8; ++i) s += r[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// IMAD.WIDE.U32 with RZ addend, operands fed back from the previous result (nothing loop-invariant to hoist:
+// round 1's k_imad_wide above had its products hoisted by ptxas and measured the IADD3 adds instead)
+__global__ void k_imad_wide_rz(uint64_t* out, uint32_t a, uint32_t b) {
+    uint32_t x[8];
+    for (int i = 0; i < 8; ++i) x[i] = threadIdx.x * 2654435761u + i + a;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint64_t w;
+            asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(x[i]), "r"(b));
+            x[i] = (uint32_t)w ^ (uint32_t)(w >> 32);
+        }
+    }
+    uint64_t s = 0; for (int i = 0; i < 8; ++i) s += x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void k_dfma(double* out, double a, double b) {
+    double r[8];
+    for (int i = 0; i < 8; ++i) r[i] = threadIdx.x + i;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(r[i]) : "d"(a), "d"(b));
+    }
+    double s = 0; for (int i = 0; i < 8; ++i) s += r[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 // 4 fused (lo.cc, hi.cc) pairs in one carry chain = 4 IMAD.WIDE.U32(.X) per "op group"
@@ -152,7 +178,11 @@ int main() {
     ms = timeit([&] { k_imad_hi<<<blocks, threads>>>((uint32_t*)buf, 3, 5); });
     printf("IMAD.HI         : %.3f ms  %.2f Tops/s  (%.1f lanes/clk/SM)\n", ms, nthreads * ITERS * 8 / ms / 1e9, nthreads * ITERS * 8 / (ms * 1e-3) / sms / 1.9e9);
     ms = timeit([&] { k_imad_wide<<<blocks, threads>>>((uint64_t*)buf, 3, 5); });
-    printf("IMAD.WIDE       : %.3f ms  %.2f Tops/s  (%.1f lanes/clk/SM)\n", ms, nthreads * ITERS * 8 / ms / 1e9, nthreads * ITERS * 8 / (ms * 1e-3) / sms / 1.9e9);
+    printf("IMAD.WIDE (hoisted by ptxas: measures IADD3): %.3f ms  %.2f Tops/s  (%.1f lanes/clk/SM)\n", ms, nthreads * ITERS * 8 / ms / 1e9, nthreads * ITERS * 8 / (ms * 1e-3) / sms / 1.9e9);
+    ms = timeit([&] { k_imad_wide_rz<<<blocks, threads>>>((uint64_t*)buf, 3, 0x9E3779B9u); });
+    printf("IMAD.WIDE (RZ addend, fed back) + LOP3: %.3f ms  %.2f T wide-ops/s  (%.1f lanes/clk/SM)\n", ms, nthreads * ITERS * 8 / ms / 1e9, nthreads * ITERS * 8 / (ms * 1e-3) / sms / 1.9e9);
+    ms = timeit([&] { k_dfma<<<blocks, threads>>>((double*)buf, 1.0000001, 0.5); });
+    printf("DFMA            : %.3f ms  %.2f Tops/s  (%.1f lanes/clk/SM)\n", ms, nthreads * ITERS * 8 / ms / 1e9, nthreads * ITERS * 8 / (ms * 1e-3) / sms / 1.9e9);
     ms = timeit([&] { k_imad_wide_cc<<<blocks, threads>>>((uint32_t*)buf, 3, 5); });
     printf("IMAD.WIDE.X x4  : %.3f ms  %.2f T wide-ops/s  (%.1f lanes/clk/SM)\n", ms, nthreads * ITERS * 4 / ms / 1e9, nthreads * ITERS * 4 / (ms * 1e-3) / sms / 1.9e9);
     ms = timeit([&] { k_iadd3<<<blocks, threads>>>((uint32_t*)buf, 3, 5); });
