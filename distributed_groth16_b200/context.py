@@ -42,12 +42,40 @@ def _ptr(arr: np.ndarray):
     return ctypes.c_void_p(arr.ctypes.data)
 
 
+class _StreamOrderedLib:
+    """The ctypes library as `Net` and the operator modules call it (`net._lib.b200zk_*`), with one rule enforced in one
+    place: every entry point that takes DEVICE pointers (`*_dev`) first makes slot 0 the caller's current torch stream
+    (`Net._t0`), so tensors produced by torch ops / NCCL and consumed by library kernels (and vice versa) are ordered on
+    one stream.  Host-buffer entry points synchronise internally and pass through untouched."""
+
+    def __init__(self, lib, net):
+        object.__setattr__(self, "_lib", lib)
+        object.__setattr__(self, "_net", net)
+        object.__setattr__(self, "_cache", {})
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if not name.endswith("_dev"):
+            return fn
+        w = self._cache.get(name)
+        if w is None:
+            net = self._net
+
+            def w(*args, _fn=fn):
+                net._t0()
+                return _fn(*args)
+            self._cache[name] = w
+        return w
+
+
 class Net:
     """One GPU party.  `Net()` picks cuda:LOCAL_RANK (or cuda:0)."""
 
     def __init__(self, device: int | None = None):
         import os
-        self._lib = _native.lib()
+        self._bound0 = None
+        self._h = None
+        self._lib = _StreamOrderedLib(_native.lib(), self)
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", "0"))
         h = c_vp()
@@ -56,6 +84,11 @@ class Net:
             raise B200zkError(rc, "cannot create a CUDA context on device %d (no CPU fallback exists)" % device)
         self._h = h
         self.device = int(device)
+        # Stream contract of every tensor-taking method: slot 0 IS torch's current stream, so torch ops, NCCL collectives
+        # and library kernels on the same tensors are ordered without the caller having to remember anything
+        # (`_t0()` re-binds when the caller switches streams).  Slots 1 / 2 are independent streams for callers that
+        # overlap several calls and synchronise explicitly (`sync(sid)`), like the reference's mux streams.
+        self._t0()
 
     # -- mpc-net::MpcNet surface that still makes sense -------------------------------------
     def party_id(self) -> int:
@@ -96,7 +129,23 @@ class Net:
 
     def use_torch_stream(self, sid: int = 0):
         import torch
-        self.check(self._lib.b200zk_ctx_set_stream(self._h, int(sid), c_vp(torch.cuda.current_stream().cuda_stream)))
+        h = torch.cuda.current_stream(self.device).cuda_stream
+        self.check(self._lib.b200zk_ctx_set_stream(self._h, int(sid), c_vp(h)))
+        if int(sid) == 0:
+            self._bound0 = h
+
+    def _t0(self):
+        """Slot 0 follows torch's current stream on this device (no-op without torch / CUDA)."""
+        try:
+            import torch
+            if not torch.cuda.is_available():
+                return
+            h = torch.cuda.current_stream(self.device).cuda_stream
+        except Exception:
+            return
+        if h != self._bound0 and self._h:
+            self.check(self._lib.b200zk_ctx_set_stream(self._h, 0, c_vp(h)))
+            self._bound0 = h
 
     def sync(self, sid: int = 0):
         self.check(self._lib.b200zk_ctx_sync(self._h, int(sid)))

@@ -469,7 +469,9 @@ static int upload(b200zk_ctx* ctx, void** dst, const void* src, size_t bytes, cu
     *dst = nullptr;
     size_t alloc = bytes == 0 ? 16 : bytes;
     B2_CUDA_OK(ctx, cudaMalloc(dst, alloc + 16));
-    if (src && bytes) B2_CUDA_OK(ctx, cudaMemcpy(*dst, src, bytes, kind));
+    // the caller's device buffers were written on slot 0's stream (the stream the library hands results back on), so the
+    // copy is ordered there; pk_build synchronises that stream before any other slot touches the key
+    if (src && bytes) B2_CUDA_OK(ctx, cudaMemcpyAsync(*dst, src, bytes, kind, ctx->slots[0].stream));
     return B200ZK_OK;
 }
 
@@ -488,6 +490,7 @@ static int pk_build(b200zk_ctx* ctx, const void* a_query, const void* b_g1_query
     if (!rc) rc = upload(ctx, &pk->l_query, l_query, (n_vars - n_inputs) * 64, kind);
     if (!rc) rc = upload(ctx, &pk->h_query, h_query, m * 64, kind);
     if (!rc) rc = upload(ctx, &pk->vk, vk_points, 56 * 8);
+    if (!rc && cudaStreamSynchronize(ctx->slots[0].stream) != cudaSuccess) rc = set_error(ctx, B200ZK_ERR_CUDA, "proving-key upload failed");
     if (rc) { b200zk_pk_free(ctx, pk); return rc; }
     const char* env = getenv("B200ZK_PK_TABLES");
     if (!(env && env[0] == '0')) {

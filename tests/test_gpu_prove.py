@@ -95,6 +95,27 @@ def test_prove_structs_mirror_reference_call_pattern(net, cref):
     assert got == exp
 
 
+def test_prove_structs_with_nonzero_r_and_s(net, cref):
+    """prove.rs:36-44,75-83,128-134 with r, s != 0: A = L + r N + MSM, B = Z + s K + MSM, C = w + u + s A + r M + r MSM(H, a)
+    (M = beta_g1 + b_g1_query[0], A = the finished A) reproduces the randomised proof of the fused prover / the oracle."""
+    from oracle import layout, bn254 as o
+    m, n_vars, n_inputs = 1 << 8, 200, 2
+    aq, b1, b2, lq, hq, vk1, vk2, z, a, b, c = _dummy_instance(cref, m, n_vars, n_inputs, 510)
+    r, s = layout.fr_to_arr([123456789])[0], layout.fr_to_arr([987654321])[0]
+    one = layout.fr_to_arr([1])[0]
+    h = ext_wit.h(PackedQAPShare(n_inputs, m - n_inputs, a, b, c, Radix2Domain(m)), None, net)
+    A = prove.A(L=aq[0], N=vk1[2], r=r, pp=None, S=aq[1:], a=z[1:]).compute(net)
+    B = prove.B(Z=b2[0], K=vk2[1], s=s, pp=None, V=b2[1:], a=z[1:]).compute(net)
+    A2, _ = cref.msm_g1(np.stack([A.limbs, vk1[0]]), np.stack([one, one]))          # a += alpha  (sha256.rs:208-212)
+    B2, _ = cref.msm_g2(np.stack([B.limbs, vk2[0]]), np.stack([one, one]))          # b += beta_g2
+    M, _ = cref.msm_g1(np.stack([vk1[1], b1[0]]), np.stack([one, one]))             # beta_g1 + b_g1_query[0]
+    C = prove.C(A=A2, M=M, s=s, r=r, pp=None, W=lq, U=hq, H=b1[1:], a=z[1:], ax=z[n_inputs:], h=h).compute(net)
+    vk = np.concatenate([vk1.reshape(-1), vk2.reshape(-1)])
+    exp = cref.groth16_prove(aq, b1, b2, lq, hq, vk, n_inputs, z, cref.h_circom(a, b, c), r, s)
+    got = o.proof_compress(layout.arr_to_g1(A2)[0], layout.arr_to_g2(B2)[0], layout.arr_to_g1(C.limbs)[0])
+    assert got == exp
+
+
 def test_f1_real_zkey_prove_on_gpu_matches_golden_and_verifies(net):
     """Fixture F1: proving key of the snarkjs-made complex-circuit-10000-10000.zkey, witness a = 3.
     The GPU proof must equal the committed golden bytes (oracle-produced, pairing-verified against the zkey's vk)
