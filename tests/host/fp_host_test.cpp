@@ -7,6 +7,7 @@
 #include "../../distributed_groth16_b200/csrc/fp.cuh"
 #include "../../distributed_groth16_b200/csrc/ec.cuh"
 #include "../../tools/experiments/ec29.cuh"
+#include "../../distributed_groth16_b200/csrc/batch_affine.cuh"
 
 extern "C" void orc_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out);
 extern "C" void orc_fr_generate(uint64_t seed, size_t n, uint64_t* out);
@@ -188,6 +189,63 @@ static int test_curve29() {
     return fails;
 }
 
+
+// ---- batch_affine.cuh: affine additions around a shared inversion (Montgomery's trick) vs the XYZZ group law ----------
+template <class C>
+static int test_batch_affine(const char* name, int is_g2) {
+    typedef typename C::F F;
+    typedef batch_affine<F> BA;
+    const int n = 48, SLOTS = 12, STEPS = 9;
+    const int PL = is_g2 ? 16 : 8;
+    uint64_t* raw = (uint64_t*)malloc(n * PL * 8);
+    if (is_g2) orc_g2_generate(31337, n, raw, 1); else orc_g1_generate(31337, n, raw, 1);
+    affine_t<F>* pts = (affine_t<F>*)raw;
+    int fails = 0;
+    for (int round = 0; round < 20; ++round) {
+        affine_t<F> acc[SLOTS];
+        xyzz_t<F> ref[SLOTS];
+        for (int k = 0; k < SLOTS; ++k) { acc[k] = affine_t<F>::infinity(); ref[k] = xyzz_t<F>::identity(); }
+        for (int step = 0; step < STEPS; ++step) {
+            affine_t<F> pt[SLOTS];
+            bool neg[SLOTS];
+            for (int k = 0; k < SLOTS; ++k) {
+                uint64_t r = rnd();
+                pt[k] = pts[r % n];
+                neg[k] = (r >> 33) & 1;
+                if (k == 1 && step == 3) pt[k] = affine_t<F>::infinity();                               // infinity operand
+                if (k == 2 && step >= 1 && step <= 2) { pt[k] = pts[5]; neg[k] = false; }                 // P + P  (doubling)
+                if (k == 2 && step == 0) { pt[k] = pts[5]; neg[k] = false; }
+                if (k == 3 && step == 0) { pt[k] = pts[6]; neg[k] = true; }                             // -P, then +P: cancels
+                if (k == 3 && step == 1) { pt[k] = pts[6]; neg[k] = false; }
+                if (k == 4 && step == 5) { pt[k] = acc[k]; neg[k] = (round & 1) != 0; }                  // acc +- acc mid-chain
+                pt[k] = BA::signed_point(pt[k], neg[k]);
+            }
+            // forward: denominators, running product
+            F d[SLOTS], pre[SLOTS], run = F::one();
+            int cs[SLOTS];
+            for (int k = 0; k < SLOTS; ++k) {
+                cs[k] = BA::prepare(acc[k], pt[k], d[k]);
+                pre[k] = run;
+                if (BA::needs_inverse(cs[k])) run = F::mul(run, d[k]);
+            }
+            F inv = F::inv(run);
+            for (int k = SLOTS - 1; k >= 0; --k) {
+                F dinv = inv;
+                if (BA::needs_inverse(cs[k])) { dinv = F::mul(inv, pre[k]); inv = F::mul(inv, d[k]); }
+                BA::finish(cs[k], acc[k], pt[k], dinv);
+            }
+            for (int k = 0; k < SLOTS; ++k) {
+                xyzz_t<F>::madd(ref[k], pt[k], false);
+                affine_t<F> ra = xyzz_t<F>::to_affine(ref[k]);
+                if (memcmp(&ra, &acc[k], sizeof(ra))) { if (fails++ < 5) printf("%s batch_affine mismatch round %d step %d slot %d\n", name, round, step, k); }
+            }
+        }
+    }
+    printf("%s batched affine additions: %d failures\n", name, fails);
+    free(raw);
+    return fails;
+}
+
 int main() {
     int fails = 0;
     fails += test_field<Fq, 0>("Fq");
@@ -197,6 +255,8 @@ int main() {
     fails += test_field29<FqParams, 0>("Fq");
     fails += test_field29<FrParams, 1>("Fr");
     fails += test_curve29();
+    fails += test_batch_affine<G1Curve>("G1", 0);
+    fails += test_batch_affine<G2Curve>("G2", 1);
     printf(fails ? "FAILED\n" : "ALL OK\n");
     return fails ? 1 : 0;
 }
