@@ -17,7 +17,6 @@
 //   6 combine    Horner over windows (c doublings each)
 #include "common.cuh"
 #include "glv.cuh"
-#include "batch_affine.cuh"
 
 namespace b200zk {
 
@@ -231,7 +230,6 @@ __global__ void k_msm_fill_tasks(const uint32_t* task_off, uint32_t nbuckets, ui
     if (g >= nbuckets) return;
     uint32_t lo = task_off[g], hi = task_off[g + 1];
     for (uint32_t t = lo; t < hi; ++t) task_bucket[t] = g;
-    if (!multi_list) return;                     // first-level chains: every bucket continues at level 2, no merge lists
     if (hi - lo > MERGE_SMALL) multi_list[atomicAdd(multi_count, 1u)] = g;
     else if (hi - lo > 1) multi_list[list_cap - 1 - atomicAdd(multi_count + 1, 1u)] = g;
 }
@@ -266,123 +264,13 @@ __global__ void k_msm_task_hist_scan(uint32_t* hist, uint32_t task_len) {      /
     uint32_t run = 0;
     for (int len = (int)task_len; len >= 0; --len) { uint32_t c = hist[len]; hist[len] = run; run += c; }
 }
-// chain_lo != nullptr (first-level chains, section 4b): also emit, in sorted-position order, where each chain's entries
-// start and how many there are, and the inverse permutation chain_pos[t] = position (the "entry list" of level 2)
 __global__ void k_msm_task_order(const uint32_t* offsets, const uint32_t* task_off, const uint32_t* task_bucket,
                                  uint32_t nbuckets, uint32_t task_len, const uint32_t* hist, const uint32_t* task_rank,
-                                 uint32_t* order, uint32_t* chain_lo, uint32_t* chain_len, uint32_t* chain_pos) {
+                                 uint32_t* order) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= task_off[nbuckets]) return;
-    uint32_t g = task_bucket[t];
-    uint32_t len = task_length(offsets, task_off, g, t, task_len);
-    uint32_t pos = hist[len] + task_rank[t];
-    order[pos] = t;
-    if (chain_lo) {
-        chain_lo[pos] = offsets[g] + (t - task_off[g]) * task_len;
-        chain_len[pos] = len;
-        chain_pos[t] = pos;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// 4b. first accumulation level: chains of <= CHAIN_LEN entries summed in AFFINE coordinates with batched inversions
-//     (batch_affine.cuh): 6 field products per addition instead of the 10 of an XYZZ mixed addition.
-//     Every bucket's sorted entry range is cut into chains (the task machinery above with task_len = CHAIN_LEN); the
-//     chains are sorted by length and dealt to blocks of CHAIN_THREADS threads x K slots: thread `tid`, slot `k` of
-//     block `b` owns the chain at sorted position b * (CHAIN_THREADS * K) + k * CHAIN_THREADS + tid (a warp touches 32
-//     consecutive positions: the running sums acc_pos[] and the prefix products pref[] are read and written coalesced).
-//     Step s adds entry s of every chain that has one.  All additions of a step in a block share ONE field inversion:
-//     each thread multiplies its slots' denominators up (forward pass, prefix products parked in pref[]), the 128 thread
-//     products go through a product tree in shared memory, thread 0 inverts the root, the tree is walked back down
-//     (inverse of a child = inverse of the parent x the sibling's product) and each thread unwinds its own slots
-//     (backward pass).  6 products per addition + ~3 per thread-step for the tree + one binary-GCD inversion per
-//     block-step (integer ALU work, off the multiplier pipe; the block waits on it, the SM's other blocks do not).
-//     The chain sums stay affine in acc_pos[]; the second level adds the few chains of every bucket with the XYZZ
-//     kernel below (bases = acc_pos, entries = chain_pos, offsets = the chain offsets per bucket).
-// ---------------------------------------------------------------------------------------------
-static const uint32_t CHAIN_LEN = 8;
-static const int CHAIN_THREADS = 128;
-
-template <class F, int K>
-__global__ void __launch_bounds__(CHAIN_THREADS, sizeof(F) > 32 ? 2 : 4) k_msm_chains_affine(
-        const affine_t<F>* bases, const uint32_t* entries, const uint32_t* chain_lo, const uint32_t* chain_len,
-        const uint32_t* nchains_ptr, affine_t<F>* acc_pos, F* pref) {
-    typedef batch_affine<F> BA;
-    __shared__ F tree[2 * CHAIN_THREADS];              // [1] root, [2 i], [2 i + 1] children of [i]; leaves at [128 + tid]
-    const uint32_t nch = *nchains_ptr;
-    const uint32_t base = blockIdx.x * (uint32_t)(CHAIN_THREADS * K);
-    if (base >= nch) return;                           // whole block
-    const uint32_t tid = threadIdx.x;
-    const uint32_t lmax = chain_len[base];             // chains are sorted by length, longest first
-    // step 0: every chain starts as its first entry
-#pragma unroll 1
-    for (int k = 0; k < K; ++k) {
-        const uint32_t p = base + k * CHAIN_THREADS + tid;
-        if (p >= nch) break;
-        const uint32_t e = entries[chain_lo[p]];
-        st16(acc_pos + p, BA::signed_point(ld16(bases + (e & 0x7FFFFFFFu)), (e >> 31) != 0));
-    }
-    for (uint32_t s = 1; s < lmax; ++s) {
-        // forward: denominators and their running product
-        F run = F::one();
-#pragma unroll 1
-        for (int k = 0; k < K; ++k) {
-            const uint32_t p = base + k * CHAIN_THREADS + tid;
-            if (p >= nch || chain_len[p] <= s) break;   // sorted: the later slots are no longer either
-            const uint32_t e = entries[chain_lo[p] + s];
-            const affine_t<F> pt = BA::signed_point(ld16(bases + (e & 0x7FFFFFFFu)), (e >> 31) != 0);
-            const affine_t<F> acc = ld16(acc_pos + p);
-            F d;
-            const int cs = BA::prepare(acc, pt, d);
-            st16(pref + p, run);
-            if (BA::needs_inverse(cs)) run = F::mul(run, d);
-        }
-        // one inversion for the block: product tree up, invert the root, inverses down
-        tree[CHAIN_THREADS + tid] = run;
-        __syncthreads();
-#pragma unroll 1
-        for (uint32_t n = CHAIN_THREADS / 2; n >= 1; n >>= 1) {
-            if (tid < n) tree[n + tid] = F::mul(tree[2 * (n + tid)], tree[2 * (n + tid) + 1]);
-            __syncthreads();
-        }
-        if (tid == 0) tree[1] = F::inv(tree[1]);
-        __syncthreads();
-#pragma unroll 1
-        for (uint32_t n = 1; n <= CHAIN_THREADS / 2; n <<= 1) {
-            if (tid < n) {
-                const uint32_t i = n + tid;
-                const F a = tree[2 * i], b = tree[2 * i + 1], v = tree[i];
-                tree[2 * i] = F::mul(v, b);
-                tree[2 * i + 1] = F::mul(v, a);
-            }
-            __syncthreads();
-        }
-        F inv = tree[CHAIN_THREADS + tid];              // 1 / (this thread's product)
-        // backward: unwind the prefix products, finish the additions
-        int kmax = 0;
-#pragma unroll 1
-        for (int k = 0; k < K; ++k) {
-            const uint32_t p = base + k * CHAIN_THREADS + tid;
-            if (p >= nch || chain_len[p] <= s) break;
-            kmax = k + 1;
-        }
-#pragma unroll 1
-        for (int k = kmax - 1; k >= 0; --k) {
-            const uint32_t p = base + k * CHAIN_THREADS + tid;
-            const uint32_t e = entries[chain_lo[p] + s];
-            const affine_t<F> pt = BA::signed_point(ld16(bases + (e & 0x7FFFFFFFu)), (e >> 31) != 0);
-            affine_t<F> acc = ld16(acc_pos + p);
-            F d;
-            const int cs = BA::prepare(acc, pt, d);
-            F dinv = inv;
-            if (BA::needs_inverse(cs)) {
-                dinv = F::mul(inv, ld16(pref + p));     // 1 / d
-                inv = F::mul(inv, d);                   // drop d from the running inverse
-            }
-            BA::finish(cs, acc, pt, dinv);
-            st16(acc_pos + p, acc);
-        }
-    }
+    uint32_t len = task_length(offsets, task_off, task_bucket[t], t, task_len);
+    order[hist[len] + task_rank[t]] = t;
 }
 
 // G2 (Fq2 coordinates): 250 registers uncapped = 8 warps/SM, fmaheavy 74% busy with `wait` the top stall
@@ -714,27 +602,21 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
     const uint32_t wsplit = (fold && nseg >= 16 * 256) ? 16 : 1;
     const size_t total = (size_t)W * n;
 
-    // window groups: `spg` consecutive bucket sets each (GLV: whole windows, i.e. both halves).  Small inputs are
-    // launch-latency bound and stay in one group.
+    // window groups: consecutive bucket sets (GLV: whole windows, i.e. both halves).  Measured (profiles/r2_msm_groups.md):
+    // at 2^20 the extra launches, the drain bubble at the end of every bucket kernel and the slowdown of the latency-bound
+    // tail kernels when they share SMs with a bucket kernel cost more than the hidden tail saves (3.94 ms with 1 group,
+    // 4.44 with 2, 5.06 with 4); from 2^22 up four groups win (15.63 -> 14.41 ms).  Fixed-base tables have one bucket set.
     unsigned ngroups = 1;
-    if (!fold && n >= (1u << 17)) {
+    if (!fold) {
         static const int g_env = getenv("B200ZK_MSM_GROUPS") ? atoi(getenv("B200ZK_MSM_GROUPS")) : 0;
-        const unsigned units = glv ? Wh : W;                 // windows
-        unsigned want = g_env > 0 ? (unsigned)g_env : 4;
-        if (want > units) want = units;
+        const unsigned nunits = glv ? Wh : W;                // windows
+        unsigned want = g_env > 0 ? (unsigned)g_env : (n >= (1u << 22) ? 4u : 1u);
+        if (want > nunits) want = nunits;
         ngroups = want;
     }
     const unsigned unit_sets = glv ? 2 : 1;
     const unsigned units = (fold ? 1 : (glv ? Wh : W));
     auto group_first_unit = [&](unsigned g) { return (unsigned)(((uint64_t)units * g) / ngroups); };   // balanced split
-
-    // Two accumulation levels for large inputs (section 4b): level 1 sums chains of <= CHAIN_LEN sorted entries in affine
-    // coordinates with batched inversions (all bucket sets in ONE launch: the batches want every chain there is),
-    // level 2 -- the window-group pipeline below -- adds the few chain sums of each bucket with the XYZZ kernel.
-    static const bool chains_env = !(getenv("B200ZK_MSM_CHAINS") && getenv("B200ZK_MSM_CHAINS")[0] == '0');
-    const bool chains = chains_env && total >= ((size_t)1 << 22) && total / CHAIN_LEN + nb < (1ull << 31);
-    const size_t max_chains = chains ? total / CHAIN_LEN + nb + 1 : 0;
-    const size_t total2 = chains ? max_chains : total;       // (bound on the) entries the group-level kernels walk
 
     // workspace carve-up (256-byte aligned)
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -742,24 +624,18 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
     // then the next power of two above 3x the average -- only outliers are split -- as long as that leaves enough
     // tasks (>= 2^19) to fill the machine
     uint32_t task_len = TASK_LEN;
-    while (task_len < MAX_TASK_LEN && (uint64_t)task_len * nb < 3 * (uint64_t)total2 &&
-           total2 / (2 * task_len) + nb >= (1u << 19))
+    while (task_len < MAX_TASK_LEN && (uint64_t)task_len * nb < 3 * (uint64_t)total &&
+           total / (2 * task_len) + nb >= (1u << 19))
         task_len *= 2;
-    const size_t max_tasks = total2 / task_len + nb + ngroups;                 // all groups together
+    const size_t max_tasks = total / task_len + nb + ngroups;                 // all groups together
     size_t o = 0;
     auto carve = [&](size_t bytes) { size_t r = o; o += al(bytes); return r; };
     const size_t o_keys = carve(total * 4), o_ranks = carve(total * 4), o_entries = carve(total * 4);
     const size_t o_counts = carve(((size_t)nb + 1) * 4), o_offsets = carve(((size_t)nb + 1) * 4);
     const size_t o_sums = carve(((size_t)nb / SCAN_TILE + 2) * 4);
-    // level 1 (chains)
-    const size_t o_c_ntasks = carve(chains ? ((size_t)nb + 1) * 4 : 0), o_c_off = carve(chains ? ((size_t)nb + 1) * 4 : 0);
-    const size_t o_c_bucket = carve(max_chains * 4), o_c_rank = carve(max_chains * 4), o_c_order = carve(max_chains * 4);
-    const size_t o_c_hist = carve(chains ? (MAX_TASK_LEN + 1) * 4 : 0);
-    const size_t o_c_lo = carve(max_chains * 4), o_c_len = carve(max_chains * 4), o_c_pos = carve(max_chains * 4);
-    const size_t o_c_acc = carve(max_chains * sizeof(affine_t<F>)), o_c_pref = carve(max_chains * sizeof(F));
     const size_t o_ntasks = carve(((size_t)nb + ngroups) * 4), o_taskoff = carve(((size_t)nb + ngroups) * 4);
     const size_t o_taskbucket = carve(max_tasks * 4);
-    const size_t o_multi = carve((total2 / task_len + 4 * ngroups + 4) * 4);
+    const size_t o_multi = carve((total / task_len + 4 * ngroups + 4) * 4);
     const size_t o_hist = carve((size_t)ngroups * (MAX_TASK_LEN + 1) * 4);
     const size_t o_rank = carve(max_tasks * 4), o_order = carve(max_tasks * 4);
     const size_t o_tasksums = carve(max_tasks * sizeof(xyzz_t<F>));
@@ -802,71 +678,7 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
     B2_CUDA_OK(ctx, cudaMemsetAsync(hist_all, 0, (size_t)ngroups * (MAX_TASK_LEN + 1) * 4, st));
     B2_CUDA_OK(ctx, cudaMemsetAsync(buckets, 0, (size_t)nb * sizeof(xyzz_t<F>), st));   // all-zero XYZZ = identity
 
-    // ---- level 1: scatter everything, cut the buckets into chains, sum the chains (one launch on acc) ------------------
-    const affine_t<F>* bases_eff = reinterpret_cast<const affine_t<F>*>(d_bases);    // what the group-level kernels gather from
-    const uint32_t* entries_eff = entries;
-    const uint32_t* offsets_eff = offsets;
     if (bases_ready) B2_CUDA_OK(ctx, cudaStreamWaitEvent(ast, bases_ready, 0));
-    if (chains) {
-        uint32_t* c_ntasks = reinterpret_cast<uint32_t*>(ws + o_c_ntasks);
-        uint32_t* c_off = reinterpret_cast<uint32_t*>(ws + o_c_off);
-        uint32_t* c_bucket = reinterpret_cast<uint32_t*>(ws + o_c_bucket);
-        uint32_t* c_rank = reinterpret_cast<uint32_t*>(ws + o_c_rank);
-        uint32_t* c_order = reinterpret_cast<uint32_t*>(ws + o_c_order);
-        uint32_t* c_hist = reinterpret_cast<uint32_t*>(ws + o_c_hist);
-        uint32_t* c_lo = reinterpret_cast<uint32_t*>(ws + o_c_lo);
-        uint32_t* c_len = reinterpret_cast<uint32_t*>(ws + o_c_len);
-        uint32_t* c_pos = reinterpret_cast<uint32_t*>(ws + o_c_pos);
-        affine_t<F>* c_acc = reinterpret_cast<affine_t<F>*>(ws + o_c_acc);
-        F* c_pref = reinterpret_cast<F*>(ws + o_c_pref);
-        {
-            LaunchScope ls(ctx, st, "msm_scatter");
-            k_msm_scatter<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(keys, ranks, offsets, (uint32_t)n, 0, total, fold ? 1u : 0u, entries);
-        }
-        B2_TRY(check_launch(ctx, "k_msm_scatter"));
-        {
-            LaunchScope ls(ctx, st, "msm_tasks");
-            k_msm_task_counts<<<(nb + 1 + 255) / 256, 256, 0, st>>>(offsets, nb, CHAIN_LEN, c_ntasks);
-        }
-        B2_TRY(exclusive_scan(ctx, st, c_ntasks, c_off, sums, nb + 1));
-        B2_CUDA_OK(ctx, cudaMemsetAsync(c_hist, 0, (MAX_TASK_LEN + 1) * 4, st));
-        {
-            LaunchScope ls(ctx, st, "msm_tasks");
-            k_msm_fill_tasks<<<(nb + 255) / 256, 256, 0, st>>>(c_off, nb, c_bucket, nullptr, 0, nullptr);
-        }
-        {
-            LaunchScope ls(ctx, st, "msm_tasks");
-            k_msm_task_hist<<<(unsigned)((max_chains + 255) / 256), 256, 0, st>>>(offsets, c_off, c_bucket, nb, CHAIN_LEN, c_hist, c_rank);
-        }
-        {
-            LaunchScope ls(ctx, st, "msm_tasks");
-            k_msm_task_hist_scan<<<1, 1, 0, st>>>(c_hist, CHAIN_LEN);
-        }
-        {
-            LaunchScope ls(ctx, st, "msm_tasks");
-            k_msm_task_order<<<(unsigned)((max_chains + 255) / 256), 256, 0, st>>>(offsets, c_off, c_bucket, nb, CHAIN_LEN, c_hist, c_rank, c_order,
-                                                                                   c_lo, c_len, c_pos);
-        }
-        B2_TRY(check_launch(ctx, "chain tables"));
-        cudaEvent_t e = next_event();
-        if (!e) return set_error(ctx, B200ZK_ERR_CUDA, "cudaEventCreate failed");
-        B2_CUDA_OK(ctx, cudaEventRecord(e, st));
-        B2_CUDA_OK(ctx, cudaStreamWaitEvent(ast, e, 0));
-        {
-            static const int k_env = getenv("B200ZK_CHAIN_K") ? atoi(getenv("B200ZK_CHAIN_K")) : 0;
-            const int K = k_env == 8 || k_env == 16 || k_env == 32 ? k_env : (max_chains >= (size_t)ctx->sm_count * 4 * CHAIN_THREADS * 16 ? 16 : 8);
-            const unsigned grid = (unsigned)((max_chains + (size_t)CHAIN_THREADS * K - 1) / ((size_t)CHAIN_THREADS * K));
-            const affine_t<F>* bp = reinterpret_cast<const affine_t<F>*>(d_bases);
-            LaunchScope ls(ctx, ast, sizeof(F) > 32 ? "msm_chains_g2" : "msm_chains_g1");
-            if (K == 8) k_msm_chains_affine<F, 8><<<grid, CHAIN_THREADS, 0, ast>>>(bp, entries, c_lo, c_len, c_off + nb, c_acc, c_pref);
-            else if (K == 16) k_msm_chains_affine<F, 16><<<grid, CHAIN_THREADS, 0, ast>>>(bp, entries, c_lo, c_len, c_off + nb, c_acc, c_pref);
-            else k_msm_chains_affine<F, 32><<<grid, CHAIN_THREADS, 0, ast>>>(bp, entries, c_lo, c_len, c_off + nb, c_acc, c_pref);
-        }
-        B2_TRY(check_launch(ctx, "k_msm_chains_affine"));
-        bases_eff = c_acc;
-        entries_eff = c_pos;
-        offsets_eff = c_off;
-    }
 
     // per-group views of the task tables
     struct Group {
@@ -883,8 +695,7 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
             const unsigned u0 = group_first_unit(g), u1 = group_first_unit(g + 1);
             G.set0 = u0 * unit_sets; G.nsets = (u1 - u0) * unit_sets;
             G.b0 = G.set0 * B; G.nbk = G.nsets * B;
-            size_t gtotal = fold ? total : (size_t)G.nsets * n;
-            if (chains) gtotal = gtotal / CHAIN_LEN + G.nbk + 1;               // chains of this group's buckets (bound)
+            const size_t gtotal = fold ? total : (size_t)G.nsets * n;
             G.task_cap = gtotal / task_len + G.nbk + 1;
             G.task_base = tb; tb += G.task_cap;
             G.list_cap = (uint32_t)(gtotal / task_len + 1);
@@ -905,7 +716,7 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
         uint32_t* hist = hist_all + (size_t)g * (MAX_TASK_LEN + 1);
         {
             LaunchScope ls(ctx, st, "msm_tasks");
-            k_msm_task_counts<<<(G.nbk + 1 + 255) / 256, 256, 0, st>>>(offsets_eff + G.b0, G.nbk, task_len, ntasks);
+            k_msm_task_counts<<<(G.nbk + 1 + 255) / 256, 256, 0, st>>>(offsets + G.b0, G.nbk, task_len, ntasks);
         }
         B2_TRY(check_launch(ctx, "k_msm_task_counts"));
         B2_TRY(exclusive_scan(ctx, st, ntasks, task_off, sums, G.nbk + 1));
@@ -917,7 +728,7 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
         B2_TRY(check_launch(ctx, "k_msm_fill_tasks"));
         {
             LaunchScope ls(ctx, st, "msm_tasks");
-            k_msm_task_hist<<<(unsigned)((G.task_cap + 255) / 256), 256, 0, st>>>(offsets_eff + G.b0, task_off, task_bucket, G.nbk, task_len, hist, task_rank);
+            k_msm_task_hist<<<(unsigned)((G.task_cap + 255) / 256), 256, 0, st>>>(offsets + G.b0, task_off, task_bucket, G.nbk, task_len, hist, task_rank);
         }
         {
             LaunchScope ls(ctx, st, "msm_tasks");
@@ -925,11 +736,10 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
         }
         {
             LaunchScope ls(ctx, st, "msm_tasks");
-            k_msm_task_order<<<(unsigned)((G.task_cap + 255) / 256), 256, 0, st>>>(offsets_eff + G.b0, task_off, task_bucket, G.nbk, task_len, hist, task_rank, order,
-                                                                                   nullptr, nullptr, nullptr);
+            k_msm_task_order<<<(unsigned)((G.task_cap + 255) / 256), 256, 0, st>>>(offsets + G.b0, task_off, task_bucket, G.nbk, task_len, hist, task_rank, order);
         }
         B2_TRY(check_launch(ctx, "k_msm_task_order"));
-        if (!chains) {
+        {
             const size_t t0 = fold ? 0 : (size_t)G.set0 * n, cnt = fold ? total : (size_t)G.nsets * n;
             LaunchScope ls(ctx, st, "msm_scatter");
             k_msm_scatter<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(keys, ranks, offsets, (uint32_t)n, t0, cnt, fold ? 1u : 0u, entries);
@@ -962,7 +772,7 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
         {
             LaunchScope ls(ctx, ast, acc_name);
             k_msm_accumulate<F><<<(unsigned)((G.task_cap + 127) / 128), 128, 0, ast>>>(
-                bases_eff, entries_eff, offsets_eff + G.b0, task_off_all + G.b0 + g, task_bucket_all + G.task_base,
+                reinterpret_cast<const affine_t<F>*>(d_bases), entries, offsets + G.b0, task_off_all + G.b0 + g, task_bucket_all + G.task_base,
                 order_all + G.task_base, G.nbk, task_len, (uint32_t)ctx->sm_count * (sizeof(F) > 32 ? B2_ACC_MINBLOCKS_G2 : B2_ACC_MINBLOCKS),
                 buckets + G.b0, task_sums_all + G.task_base);
         }

@@ -7,7 +7,7 @@
 #include "../../distributed_groth16_b200/csrc/fp.cuh"
 #include "../../distributed_groth16_b200/csrc/ec.cuh"
 #include "../../tools/experiments/ec29.cuh"
-#include "../../distributed_groth16_b200/csrc/batch_affine.cuh"
+#include "../../tools/experiments/batch_affine.cuh"
 
 extern "C" void orc_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out);
 extern "C" void orc_fr_generate(uint64_t seed, size_t n, uint64_t* out);

@@ -1,5 +1,5 @@
-// batch_affine.cuh -- affine point additions with a shared (batched) inversion, the arithmetic of the first bucket
-// accumulation level (msm.cu, "chains").
+// batch_affine.cuh -- EXPERIMENT (see msm_chains.cuh for the outcome): affine point additions with a shared (batched)
+// inversion, the arithmetic of a first bucket accumulation level made of "chains".
 //
 // Replaces the bucket additions inside arkworks' `VariableBaseMSM` (reached from
 // /root/reference/dist-primitives/src/dmsm/mod.rs:82).  An XYZZ mixed addition costs 8M + 2S = 10 field products;
@@ -15,7 +15,7 @@
 // Infinity is the all-zero pair (the zkey convention, ark-circom/src/zkey.rs:353-373; not on y^2 = x^3 + b).
 // Everything is B2_HD and unit-tested on the host against the XYZZ group law (tests/host/fp_host_test.cpp).
 #pragma once
-#include "ec.cuh"
+#include "../../distributed_groth16_b200/csrc/ec.cuh"
 
 namespace b200zk {
 
