@@ -97,6 +97,20 @@ SIGNATURES = {
     "b200zk_g1_generate_dev": (ctypes.c_int, [c_vp, ctypes.c_uint64, ctypes.c_size_t, c_vp]),
     "b200zk_g2_generate_dev": (ctypes.c_int, [c_vp, ctypes.c_uint64, ctypes.c_size_t, c_vp]),
     "b200zk_fr_generate_dev": (ctypes.c_int, [c_vp, ctypes.c_uint64, ctypes.c_size_t, c_vp]),
+    "b200zk_group_create": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "b200zk_group_destroy": (None, [c_vp]),
+    "b200zk_group_size": (ctypes.c_int, [c_vp]),
+    "b200zk_group_ctx": (c_vp, [c_vp, ctypes.c_int]),
+    "b200zk_group_last_error": (ctypes.c_char_p, [c_vp]),
+    "b200zk_group_msm_g1": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, c_vp, ctypes.c_size_t, c_vp, ctypes.POINTER(ctypes.c_int)]),
+    "b200zk_group_msm_g2": (ctypes.c_int, [c_vp, c_vp, ctypes.c_size_t, c_vp, ctypes.c_size_t, c_vp, ctypes.POINTER(ctypes.c_int)]),
+    "b200zk_group_ntt_fr": (ctypes.c_int, [c_vp, c_vp, ctypes.c_uint, ctypes.c_int]),
+    "b200zk_group_h_circom": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, ctypes.c_uint, c_vp]),
+    "b200zk_group_pk_upload": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.c_size_t, ctypes.c_size_t,
+                                              ctypes.c_size_t, c_vp, ctypes.POINTER(c_vp)]),
+    "b200zk_group_pk_free": (None, [c_vp, c_vp]),
+    "b200zk_group_pk_table_bytes": (ctypes.c_size_t, [c_vp]),
+    "b200zk_group_groth16_prove": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "b200zk_test_field_op": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp, ctypes.c_size_t]),
 }
 

@@ -29,6 +29,8 @@ extern "C" {
 
 typedef struct b200zk_ctx b200zk_ctx;
 typedef struct b200zk_pk b200zk_pk;
+typedef struct b200zk_group b200zk_group;         /* several GPUs of one box, one host process (csrc/group.cu) */
+typedef struct b200zk_group_pk b200zk_group_pk;   /* a proving key sharded over a group */
 
 enum {
     B200ZK_OK = 0,
@@ -235,6 +237,39 @@ int b200zk_fr_lincomb_dev(b200zk_ctx* ctx, const void* d_a, const void* d_b, con
 int b200zk_g1_generate_dev(b200zk_ctx* ctx, uint64_t seed, size_t n, void* d_out);
 int b200zk_g2_generate_dev(b200zk_ctx* ctx, uint64_t seed, size_t n, void* d_out);
 int b200zk_fr_generate_dev(b200zk_ctx* ctx, uint64_t seed, size_t n, void* d_out);
+
+/* ---- multi-GPU group: the sharded hot path behind ONE call each (SURVEY 8b `device_ids, n_dev`; BASELINE config 5) ------
+ * One host process owns n_dev GPUs (1, 2, 4 or 8) with NVLink peer access; the king/client star of mpc-net/src/lib.rs:61-139
+ * is replaced by index-range sharding of the MSMs and a four-step NTT whose column kernels store straight into the owning
+ * peer's memory.  Host buffers hold the WHOLE vectors (what the Rust caller has); results are the same group elements /
+ * field vectors / proof bytes as the single-GPU calls.  Calls on one group are serialised by the caller. */
+int b200zk_group_create(const int* device_ids, int n_dev, b200zk_group** out);
+void b200zk_group_destroy(b200zk_group* group);
+int b200zk_group_size(const b200zk_group* group);
+b200zk_ctx* b200zk_group_ctx(b200zk_group* group, int rank);            /* rank's single-GPU context (borrowed) */
+const char* b200zk_group_last_error(const b200zk_group* group);
+/* d_msm (dist-primitives/src/dmsm/mod.rs:70-98) over all GPUs of the group. */
+int b200zk_group_msm_g1(b200zk_group* group, const uint64_t* bases, size_t n_bases, const uint64_t* scalars, size_t n_scalars,
+                        uint64_t out_affine[8], int* out_is_inf);
+int b200zk_group_msm_g2(b200zk_group* group, const uint64_t* bases, size_t n_bases, const uint64_t* scalars, size_t n_scalars,
+                        uint64_t out_affine[16], int* out_is_inf);
+/* d_fft / d_ifft (dist-primitives/src/dfft/mod.rs:17-95): natural order in and out, in place, 2^log_n elements. */
+int b200zk_group_ntt_fr(b200zk_group* group, uint64_t* data, unsigned log_n, int inverse);
+/* ext_wit::h (groth16/src/ext_wit.rs:16-101): a, b, c, h_out: 2^log_m x 4 limbs. */
+int b200zk_group_h_circom(b200zk_group* group, const uint64_t* a, const uint64_t* b, const uint64_t* c, unsigned log_m,
+                          uint64_t* h_out);
+/* Proving key sharded over the group (arguments as b200zk_pk_upload): GPU g keeps rows [g n / P, (g+1) n / P) of every
+ * query (h_query in the column layout of the sharded h) plus their fixed-base tables. */
+int b200zk_group_pk_upload(b200zk_group* group, const uint64_t* a_query, const uint64_t* b_g1_query, const uint64_t* b_g2_query,
+                           const uint64_t* l_query, const uint64_t* h_query, size_t n_vars, size_t n_inputs, size_t m,
+                           const uint64_t* vk_points, b200zk_group_pk** out);
+void b200zk_group_pk_free(b200zk_group* group, b200zk_group_pk* pk);
+size_t b200zk_group_pk_table_bytes(const b200zk_group_pk* pk);
+/* prove::{A,B,C} + assembly + Compress::Yes (groth16/src/prove.rs:21-136, examples/sha256.rs:208-212), arguments as
+ * b200zk_groth16_prove: sharded h, five partial MSMs per GPU, peer copies of the partials to GPU 0, assembly there. */
+int b200zk_group_groth16_prove(b200zk_group* group, const b200zk_group_pk* pk, const uint64_t* z, const uint64_t* a,
+                               const uint64_t* b, const uint64_t* c, const uint64_t r[4], const uint64_t s[4],
+                               uint8_t proof_out[128]);
 
 /* ---- self-test hooks (tests only): element-wise field ops on device ------------------------- */
 /* op: 0 mul, 1 add, 2 sub; field: 0 Fq, 1 Fr.  a, b, out: n x 4 limbs host buffers. */
