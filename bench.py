@@ -184,6 +184,13 @@ def measure_prove(net, args, with_cpu):
            "msm_sizes": {"g1": [n_vars - 1, n_vars - n_inputs, m], "g2": [n_vars - 1]},
            "pk_table_gb": pk.table_bytes / 2**30,
            "timing": "host wall clock around b200zk_groth16_prove_dev (includes the D2H of the proof), 5 runs after 2 warm-ups"}
+    # 6 x 64 m (3 iNTT + 3 coset NTT) + 4 x 32 m (pointwise) + 96 (n_vars - 1) [A] + 160 (n_vars - 1) [B]
+    # + 96 n_aux [L] + 96 m [H-query]; the r-dependent b_g1 MSM does not run with r = 0
+    alg = 6 * 64 * m + 4 * 32 * m + 96 * (n_vars - 1) + 160 * (n_vars - 1) + 96 * (n_vars - n_inputs) + 96 * m
+    peak, peak_src = _peaks()
+    res["roofline"] = {"bound": "hbm", "achieved": alg / (res["ms"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                       "frac": alg / (res["ms"] * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg, "peak_source": peak_src,
+                       "note": "whole proof (h pipeline + 4 MSMs + assembly); multiplier-pipe bound like its kernels"}
     if with_cpu:
         from oracle import cref
         ncores = os.cpu_count() or 1
@@ -197,6 +204,272 @@ def measure_prove(net, args, with_cpu):
         res["bit_exact_vs_cpu"] = bool(exp == proof)
     pk.free()
     return res
+
+
+def measure_prove_sha256(net, with_cpu):
+    """BASELINE config 4: the reference's own workload (groth16/examples/sha256.rs:158-169 "Arkworks Proof" timer;
+    zk-cli/README.md:42): sha256 circuit, m = 2^15, r = s = 0.  The key is made by the product's GPU setup from a toxic waste;
+    with the CPU baseline enabled the toxic waste and generators are the ones the reference's seed [42; 32] yields
+    (oracle/ark_rand.py), so the GPU proof must be the reference's committed proof.bin byte for byte."""
+    import numpy as np
+    from distributed_groth16_b200.groth16 import circom, setup
+    gold_dir = os.path.join(ROOT, "tests", "golden")
+    d = np.load(os.path.join(gold_dir, "sha256_circuit.npz"))
+    n_wires, n_pub, n_cons = (int(x) for x in d["dims"])
+    n_inputs = n_pub + 1
+    m = 1
+    while m < n_cons + n_inputs:
+        m <<= 1
+    coo = lambda k: (d[k + "_rows"], d[k + "_cols"], d[k + "_vals"])
+    gens = {}
+    toxic = (0x1234567, 0x2345678, 0x3456789, 0x456789A, 0x56789AB)
+    if with_cpu:
+        from oracle import ark_rand as ar, layout, reference_instance
+        tw = ar.groth16_toxic_waste(reference_instance.SEED, m)
+        toxic = (tw["t"], tw["alpha"], tw["beta"], tw["gamma"], tw["delta"])
+        gens = dict(g1_generator=layout.g1_to_arr([tw["g1"]])[0], g2_generator=layout.g2_to_arr([tw["g2"]])[0])
+    t0 = time.perf_counter()
+    pk, vk, mats = setup.circuit_specific_setup(net, n_wires, n_inputs, n_cons, coo("a"), coo("b"), coo("c"), toxic, **gens)
+    setup_ms = (time.perf_counter() - t0) * 1e3
+    z = net.fr_convert(net.to_device(d["witness"]), to_mont=True)
+    zero = np.zeros(4, dtype=np.uint64)
+    ts, proof = [], None
+    for _ in range(2 + 7):
+        net.sync(0)
+        t0 = time.perf_counter()
+        proof = circom.prove_from_matrices(pk, mats, z, zero, zero)
+        ts.append((time.perf_counter() - t0) * 1e3)
+    ts = sorted(ts[2:])
+    pk.free()
+    res = {"metric": "Groth16 prove, reference sha256 circuit (BN254, %d constraints, m = 2^%d, r = s = 0)" % (n_cons, m.bit_length() - 1),
+           "ms": ts[len(ts) // 2], "ms_min": ts[0], "unit": "ms", "higher_is_better": False, "gpu_setup_ms": setup_ms,
+           "msm_sizes": {"g1": [n_wires - 1, n_wires - n_inputs, m], "g2": [n_wires - 1]},
+           "timing": "host wall clock around qap() + b200zk_groth16_prove_dev (witness resident, proof bytes on the host), 7 runs after 2"}
+    if with_cpu:
+        from oracle import cref, reference_instance
+        gold = open(os.path.join(gold_dir, "sha256_proof.bin"), "rb").read()
+        res["bytes_equal_reference_proof_bin"] = bool(proof == gold)
+        cpk, cvk, cz, ca, cb, cc, _ = reference_instance.sha256_instance(cref, gold_dir)
+        vk_pts = np.concatenate([cvk["alpha_g1"], cvk["beta_g1"], cvk["delta_g1"], cvk["beta_g2"], cvk["delta_g2"]])
+        ncores = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        got = cref.groth16_prove(cpk["a_query"], cpk["b_g1_query"], cpk["b_g2_query"], cpk["l_query"], cpk["h_query"], vk_pts, n_inputs,
+                                 cz, cref.h_circom(ca, cb, cc, ncores), zero, zero, mirror_bg1=False, nthreads=ncores)
+        res["cpu_baseline"] = {"ms": (time.perf_counter() - t0) * 1e3, "cores": ncores, "kind": "port",
+                               "sample": "one full prove (h + 4 MSMs) with the CPU restatement; bytes == proof.bin: %s" % (got == gold)}
+    return res
+
+
+def measure_msm_sizes(net, dev, log_sizes):
+    """north_star's size sweep on one GPU (the reference's own loop: dist-primitives/examples/dmsm_bench.rs:45-50): generic
+    d_msm and the fixed-base-table MSM at every size, device time (CUDA events), inputs resident."""
+    import torch
+    out = {}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for log_n in log_sizes:
+        n = 1 << log_n
+        try:
+            bases, scalars = net.generate_g1(0xB2000002, n), net.generate_fr(0xB2000002, n)
+            part = torch.empty(16, dtype=torch.int64, device=dev)
+
+            def timed(fn, reps):
+                fn()
+                evs = []
+                for _ in range(reps):
+                    flush.fill_(1)
+                    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a0.record()
+                    fn()
+                    a1.record()
+                    evs.append((a0, a1))
+                torch.cuda.synchronize()
+                t = sorted(x.elapsed_time(y) for x, y in evs)
+                return t[len(t) // 2], t[0]
+            reps = 5 if log_n <= 22 else 3
+            ms, ms_min = timed(lambda: net.msm_dev(bases, scalars, part), reps)
+            gen = net.sum_points_dev(part, 1)
+            row = {"generic": {"ms": ms, "ms_min": ms_min, "mpairs_s": n / ms / 1e3,
+                               "hbm_frac": 96.0 * n / (ms * 1e-3) / 1e9 / _peaks()[0]}}
+            c_tab = net.msm_table_auto_window(n)
+            table = net.msm_table_build(bases, c_tab)
+            tms, tmin = timed(lambda: net.msm_table_dev(table, scalars, c_tab, part), reps)
+            tab = net.sum_points_dev(part, 1)
+            row["fixed_base"] = {"ms": tms, "ms_min": tmin, "mpairs_s": n / tms / 1e3, "window": c_tab,
+                                 "table_gb": table.numel() * 8 / 2**30, "bit_exact_vs_generic": bool((tab[0] == gen[0]).all())}
+            del table, bases, scalars
+            torch.cuda.empty_cache()
+            out["2^%d" % log_n] = row
+        except Exception as e:                                 # e.g. out of memory on a smaller part: report, do not fail the line
+            out["2^%d" % log_n] = {"error": str(e)[:200]}
+    return out
+
+
+def _cols_layout(t, ncols, world, rank):
+    """device tensor (N, w) -> this rank's column layout (ncols / world, N / ncols, w)   (parallel.py)."""
+    n, w = t.shape
+    cg = ncols // world
+    return t.reshape(n // ncols, ncols, w)[:, rank * cg:(rank + 1) * cg].permute(1, 0, 2).contiguous()
+
+
+def _max_ms(times, dev):
+    """median over iterations, max over ranks"""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(sorted(times)[len(times) // 2], device=dev, dtype=torch.float64)
+    if dist.is_initialized():
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t)
+
+
+def measure_multi_gpu(net, dev, rank, world, with_cpu):
+    """The collectives north_star names, on the clock: four-step NTT (NCCL all-to-all vs fused peer stores), the sharded
+    Groth16 prover (BASELINE config 5) and strong-scaling MSMs.  Device-event times, max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from distributed_groth16_b200 import parallel as par
+    from distributed_groth16_b200._constants import FR_ONE_MONT
+    out = {}
+
+    def ev_time(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        ts = []
+        for _ in range(reps):
+            dist.barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            fn()
+            a1.record()
+            a1.synchronize()
+            ts.append(a0.elapsed_time(a1))
+        return _max_ms(ts, dev)
+
+    # ---- four-step NTT, 2^24 elements over all ranks ----------------------------------------------------------------------
+    log_n = int(os.environ.get("B200ZK_BENCH_FOURSTEP_LOG_N", "24"))
+    log_rows, log_cols = par.split_log(log_n)
+    rows, cols = 1 << log_rows, 1 << log_cols
+    cg = cols // world
+    loc = net.generate_fr(0xB2000003 + rank, cg * rows).reshape(cg, rows, 4)
+    be = par.GpuBackend(net)
+    xch = par.P2PExchange(net, max(rows, cols) * max(rows, cols) // world)
+    y_nccl = par.sharded_ntt(be, loc, log_rows, log_cols)
+    y_p2p = par.sharded_ntt_p2p(net, xch, loc, log_rows, log_cols)
+    same = bool((y_nccl == y_p2p).all())
+    back = par.sharded_ntt_p2p(net, xch, y_p2p, log_cols, log_rows, inverse=True)
+    round_trip = bool((back == loc).all())
+    flags = torch.tensor([int(same), int(round_trip)], device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    ms_nccl = ev_time(lambda: par.sharded_ntt(be, loc, log_rows, log_cols))
+    ms_p2p = ev_time(lambda: par.sharded_ntt_p2p(net, xch, loc, log_rows, log_cols))
+    ms_cols = ev_time(lambda: be.batched_ntt_post(loc.reshape(cg * rows, 4), log_rows, cg, False, log_base=log_n, b0=rank * cg, alpha=1))
+    moved = (1 << log_n) // world * 32 * (world - 1) // world             # bytes each GPU sends (and receives)
+    out["ntt_fourstep"] = {
+        "log_n": log_n, "ms_nccl_all_to_all": ms_nccl, "ms_fused_p2p": ms_p2p, "ms_local_column_pass_only": ms_cols,
+        "gelem_s_fused": (1 << log_n) / ms_p2p / 1e6, "bytes_sent_per_gpu": moved,
+        "exchange_share_nccl": max(0.0, 1.0 - 2 * ms_cols / ms_nccl),
+        "nvlink_gbs_per_gpu_if_exchange_alone": moved / max(ms_nccl - 2 * ms_cols, 1e-3) / 1e6,
+        "nccl_equals_fused": bool(flags[0].item()), "inverse_round_trip_exact": bool(flags[1].item()),
+        "how": "vector in the column layout of parallel.py; NCCL arm = column NTTs + all_to_all_single + row NTTs, fused arm = the "
+               "column kernels' last pass stores into the owners' buffers over NVLink (no pack / all-to-all / unpack); "
+               "exchange_share = 1 - 2 x (column pass alone) / whole transform"}
+    del y_nccl, y_p2p, back, loc
+
+    # ---- BASELINE config 5: sharded Groth16 prove ---------------------------------------------------------------------------
+    log_m = int(os.environ.get("B200ZK_BENCH_SHARDED_LOG_M", "24"))
+    m = 1 << log_m
+    n_vars, n_inputs = m, 2
+    n_aux = n_vars - n_inputs
+    lr, lc = par.split_log(log_m)
+    pcols = 1 << lc
+    sl = slice(rank * n_vars // world, (rank + 1) * n_vars // world)
+    sla = slice(rank * n_aux // world, (rank + 1) * n_aux // world)
+    # the global dummy instance is generated on every rank (same seeds) and sliced; rank 0 keeps it for the single-GPU check
+    aq, b1 = net.generate_g1(301, n_vars), net.generate_g1(302, n_vars)
+    b2 = net.generate_g2(303, n_vars)
+    lq, hq = net.generate_g1(304, n_aux), net.generate_g1(305, m)
+    vk = np.concatenate([net.generate_g1(306, 3).cpu().numpy().view(np.uint64).reshape(-1),
+                         net.generate_g2(307, 2).cpu().numpy().view(np.uint64).reshape(-1)])
+    z = net.generate_fr(308, n_vars)
+    z[0] = torch.from_numpy(np.array(FR_ONE_MONT, dtype=np.uint64).view(np.int64)).to(dev)
+    a, b, c = (net.generate_fr(sd, m) for sd in (309, 310, 311))
+    spk = par.ShardedProvingKey(net, aq[sl].contiguous(), b1[sl].contiguous(), b2[sl].contiguous(), lq[sla].contiguous(),
+                                _cols_layout(hq, pcols, world, rank), n_inputs, vk)
+    z_sh, zaux_sh = z[sl].contiguous(), z[n_inputs:][sla].contiguous()
+    la, lb, lc_ = (_cols_layout(v, pcols, world, rank) for v in (a, b, c))
+    if rank != 0:
+        del aq, b1, b2, lq, hq, a, b, c, z
+        torch.cuda.empty_cache()
+    xch2 = par.P2PExchange(net, (1 << lr) * (1 << lr) // world)
+    proofs = {}
+    res = {"log_m": log_m, "fixed_base_table_gb_per_gpu": sum(t.numel() * 8 for t, _ in spk.tables.values()) / 2**30}
+    for mode, x in (("nccl_all_to_all", None), ("fused_p2p", xch2)):
+        ts = []
+        for it in range(2 + 3):
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            proofs[mode] = par.sharded_prove(net, spk, z_sh, zaux_sh, la, lb, lc_, log_m, xch=x)
+            torch.cuda.synchronize()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        res["ms_" + mode] = _max_ms(ts[2:], dev)
+        hs = []
+        for it in range(1 + 3):
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            (par.sharded_h(be, la, lb, lc_, log_m) if x is None else par.sharded_h_p2p(net, x, la, lb, lc_, log_m))
+            torch.cuda.synchronize()
+            hs.append((time.perf_counter() - t0) * 1e3)
+        res["ms_h_pipeline_" + mode] = _max_ms(hs[1:], dev)
+    res["nccl_equals_fused"] = bool(proofs["nccl_all_to_all"] == proofs["fused_p2p"])
+    alg = 6 * 64 * m + 4 * 32 * m + 96 * n_vars + 160 * n_vars + 96 * n_aux + 96 * m
+    peak, _ = _peaks()
+    res["roofline"] = {"bound": "hbm", "achieved": alg / (res["ms_fused_p2p"] * 1e-3) / 1e9, "peak": peak * world, "unit": "GB/s",
+                       "frac": alg / (res["ms_fused_p2p"] * 1e-3) / 1e9 / (peak * world), "algorithmic_bytes": alg}
+    res["timing"] = "host wall clock between barriers + device syncs around parallel.sharded_prove (proof bytes on every host), max over ranks"
+    if rank == 0:
+        try:
+            from distributed_groth16_b200.groth16 import ProvingKey, prove
+            pk = ProvingKey.from_device(net, aq, b1, b2, lq, hq, n_inputs, vk)
+            ts = []
+            for it in range(3):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                single = prove.create_proof_dev(pk, z, a, b, c)
+                ts.append((time.perf_counter() - t0) * 1e3)
+            res["ms_single_gpu"] = sorted(ts)[1]
+            res["single_gpu_table_gb"] = pk.table_bytes / 2**30
+            res["bytes_equal_single_gpu_proof"] = bool(single == proofs["fused_p2p"])
+            pk.free()
+        except Exception as e:
+            res["single_gpu_check"] = "skipped: " + str(e)[:160]
+        del aq, b1, b2, lq, hq, a, b, c, z
+    torch.cuda.empty_cache()
+    dist.barrier()
+    out["prove_sharded"] = res
+    del spk, la, lb, lc_, z_sh, zaux_sh
+    torch.cuda.empty_cache()
+
+    # ---- strong scaling: a fixed total number of pairs split over the ranks ---------------------------------------------------
+    from distributed_groth16_b200.parallel import PartialExchange
+    xp = PartialExchange(net)
+    strong = {}
+    for log_t in (24, 26):
+        n_loc = (1 << log_t) // world
+        bases, scalars = net.generate_g1(0xB2000002 + (rank << 24) + log_t, n_loc), net.generate_fr(0xB2000002 + rank * 7 + log_t, n_loc)
+        part = torch.empty(16, dtype=torch.int64, device=dev)
+        res_t = torch.empty(9, dtype=torch.int64, device=dev)
+
+        def step():
+            net.msm_dev(bases, scalars, part)
+            xp.sum(part, out=res_t)
+        ms = ev_time(step, reps=3, warm=1)
+        strong["2^%d" % log_t] = {"pairs_per_gpu": n_loc, "ms": ms, "mpairs_s": (1 << log_t) / ms / 1e3}
+        del bases, scalars
+        torch.cuda.empty_cache()
+    out["msm_strong"] = strong
+    return out
 
 
 _JSON_FD = None
@@ -233,7 +506,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-prove", action="store_true", help="skip the secondary Groth16-prove measurement")
+    ap.add_argument("--no-prove", action="store_true", help="skip the secondary Groth16-prove measurements")
+    ap.add_argument("--no-multi", action="store_true", help="N > 1: skip the four-step NTT / sharded prove / strong-scaling sections")
+    ap.add_argument("--no-sizes", action="store_true", help="N = 1: skip the 2^22..2^26 MSM size sweep")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -260,19 +535,27 @@ def main():
     bases = net.generate_g1(0xB2000002 + rank * 0x1000000, n)
     scalars = net.generate_fr(0xB2000002 + rank, n)
     part = torch.empty(16, dtype=torch.int64, device=dev)
-    gathered = torch.empty((world, 16), dtype=torch.int64, device=dev)
+    res_dev = torch.empty(9, dtype=torch.int64, device=dev)          # affine result + infinity flag (multi-GPU exchange kernel)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    xch = None
+    if world > 1:
+        from distributed_groth16_b200.parallel import PartialExchange
+        xch = PartialExchange(net)        # peer mailboxes: d_msm's exchange is ONE kernel over NVLink stores, no NCCL call per step
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def host_result():
+        r = res_dev.cpu().numpy().view(np.uint64)
+        return r[:8].copy(), bool(r[8])
+
     def step_resident():
         net.msm_dev(bases, scalars, part)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, part.reshape(1, -1))
-            return net.sum_points_dev(gathered, world)
+            xch.sum(part, out=res_dev)            # publish to every peer, wait for theirs, add, normalise: stays on the device
+            return None
         return net.sum_points_dev(part, 1)
 
     # pinned host copies for the e2e arm
@@ -290,8 +573,8 @@ def main():
         d_b2.copy_(h_bases, non_blocking=True)
         d_s2.copy_(h_scalars, non_blocking=True)
         net.msm_dev(d_b2, d_s2, part)
-        dist.all_gather_into_tensor(gathered, part.reshape(1, -1))
-        return net.sum_points_dev(gathered, world)
+        xch.sum(part, out=res_dev)
+        return host_result()                                   # D2H of the affine result: the step's output reaches the host
 
     def timed(fn, steps):
         times = []
@@ -328,6 +611,8 @@ def main():
     times_e2e, res_e2e = timed(step_e2e, max(3, min(args.steps, 10)))
     barrier()
     ms_e2e = sum(times_e2e) / len(times_e2e)
+    if world > 1:
+        res = host_result()
     assert (res[0] == res_e2e[0]).all()
 
     # steady-state throughput with the steps issued round-robin over the three stream slots, i.e. the way the
@@ -403,10 +688,26 @@ def main():
     rep = net.profile_report()
     net.profile(False)
 
+    multi = None
+    gathered_inputs = None
     if world > 1:
         t = torch.tensor([ms_step, ms_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_step, ms_e2e = float(t[0]), float(t[1])
+        if not args.no_cpu_baseline:
+            # every rank's inputs go to rank 0, which checks the N-GPU result against the CPU restatement on the whole input
+            gb = [torch.empty_like(bases) for _ in range(world)] if rank == 0 else None
+            gs = [torch.empty_like(scalars) for _ in range(world)] if rank == 0 else None
+            dist.gather(bases, gb, dst=0)
+            dist.gather(scalars, gs, dst=0)
+            if rank == 0:
+                gathered_inputs = (np.concatenate([x.cpu().numpy().view(np.uint64) for x in gb]),
+                                   np.concatenate([x.cpu().numpy().view(np.uint64) for x in gs]))
+                del gb, gs
+        del bases, scalars, d_b2, d_s2
+        torch.cuda.empty_cache()
+        if not args.no_multi:
+            multi = measure_multi_gpu(net, dev, rank, world, not args.no_cpu_baseline)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -437,7 +738,8 @@ def main():
         "dtype": "u32x8 Montgomery (256-bit modular integers)", "data": "synthetic",
         "config": {"workload": WORKLOAD,
                    "pairs_per_gpu": n, "l2": "256 MiB flush write between timed iterations; inputs+workspace > L2",
-                   "parallelism": "length-sharded x%d, all-gather of XYZZ partials" % world},
+                   "parallelism": "length-sharded x%d; partials exchanged by one kernel over NVLink peer mailboxes "
+                                  "(b200zk_msm_exchange_sum_dev), no NCCL call in the step" % world},
         "e2e": {"value": world * n / ms_e2e / 1e3, "unit": UNIT, "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": n * 96, "d2h_bytes_per_step": 72},
         "gpu_launches": int(launches),
@@ -464,19 +766,29 @@ def main():
     if not args.no_cpu_baseline:
         from oracle import cref                                  # cpu_baseline leg: the checker timed as a baseline
         cref.build()
-        hb = bases.cpu().numpy().view(np.uint64)
-        hs = scalars.cpu().numpy().view(np.uint64)
+        if world == 1:
+            hb, hs = bases.cpu().numpy().view(np.uint64), scalars.cpu().numpy().view(np.uint64)
+        else:
+            hb, hs = gathered_inputs
         t0 = time.perf_counter()
         ncores = os.cpu_count() or cref.num_threads()
         exp, _ = cref.msm_g1(hb, hs, ncores)
         dt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": n / dt / 1e6, "unit": UNIT, "cores": ncores, "kind": "port",
-                               "sample": "one full 2^%d-pair G1 MSM, all host threads (%.2f s)" % (LOG_N, dt),
-                               "bit_exact_vs_gpu": bool(world == 1 and (exp == res[0]).all()) if world == 1 else None}
+        out["cpu_baseline"] = {"value": hb.shape[0] / dt / 1e6, "unit": UNIT, "cores": ncores, "kind": "port",
+                               "sample": "one full %d x 2^%d-pair G1 MSM (all ranks' inputs), arkworks-equivalent CPU restatement, "
+                                         "all host threads (%.2f s)" % (world, LOG_N, dt),
+                               "bit_exact_vs_gpu": bool((exp == res[0]).all())}
+    if multi:
+        out.update(multi)
     if world == 1:
         out["ntt"] = measure_ntt(net, peak, pipe_peak)
     if world == 1 and not args.no_prove:
         out["prove"] = measure_prove(net, args, not args.no_cpu_baseline)
+        out["prove_sha256"] = measure_prove_sha256(net, not args.no_cpu_baseline)
+    if world == 1 and not args.no_sizes:
+        del bases, scalars
+        torch.cuda.empty_cache()
+        out["msm_sizes"] = measure_msm_sizes(net, dev, (22, 24, 26))
     emit(out)
     if world > 1:
         dist.destroy_process_group()

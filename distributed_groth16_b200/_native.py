@@ -63,6 +63,8 @@ SIGNATURES = {
     "b200zk_peer_open": (ctypes.c_int, [c_vp, c_vp, ctypes.POINTER(c_vp)]),
     "b200zk_peer_close": (ctypes.c_int, [c_vp, c_vp]),
     "b200zk_peer_free": (ctypes.c_int, [c_vp, c_vp]),
+    "b200zk_msm_exchange_sum_dev": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, ctypes.POINTER(c_vp), ctypes.c_uint,
+                                                   ctypes.c_uint, ctypes.c_uint64, c_vp]),
     "b200zk_ntt_fr_batched_post_dev": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_uint, ctypes.c_uint,
                                                       ctypes.c_int, ctypes.c_uint, ctypes.c_int, ctypes.c_uint64,
                                                       ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64]),

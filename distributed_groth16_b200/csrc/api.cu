@@ -263,6 +263,7 @@ static int sum_host(b200zk_ctx* ctx, int stream, const void* d_xyzz, size_t coun
     const size_t PB = G2 ? 128 : 64;
     Slot& sl = ctx->slots[stream];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     B2_CUDA_OK(ctx, sl.small.reserve(1024));
     char* sm = reinterpret_cast<char*>(sl.small.p);
     B2_TRY(G2 ? g2_sum_dev(ctx, sl, d_xyzz, count, sm) : g1_sum_dev(ctx, sl, d_xyzz, count, sm));
@@ -289,12 +290,14 @@ int b200zk_msm_g1_dev(b200zk_ctx* ctx, int stream, const void* d_bases, const vo
     if (!ctx || !valid_slot(stream) || !d_out) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[stream];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     return msm_g1_dev(ctx, sl, d_bases, d_scalars, n, d_out);
 }
 int b200zk_msm_g2_dev(b200zk_ctx* ctx, int stream, const void* d_bases, const void* d_scalars, size_t n, void* d_out) {
     if (!ctx || !valid_slot(stream) || !d_out) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[stream];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     return msm_g2_dev(ctx, sl, d_bases, d_scalars, n, d_out);
 }
 
@@ -304,6 +307,7 @@ int b200zk_msm_table_build_dev(b200zk_ctx* ctx, int stream, int g2, const void* 
     if (!ctx || !valid_slot(stream) || (n && (!d_bases || !d_table))) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[stream];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     return msm_table_build_dev(ctx, sl, g2, d_bases, n, c, d_table);
 }
 int b200zk_msm_table_dev(b200zk_ctx* ctx, int stream, int g2, const void* d_table, const void* d_scalars, size_t n, unsigned c,
@@ -311,6 +315,7 @@ int b200zk_msm_table_dev(b200zk_ctx* ctx, int stream, int g2, const void* d_tabl
     if (!ctx || !valid_slot(stream) || !d_out) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[stream];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     return msm_table_dev(ctx, sl, g2, d_table, d_scalars, n, c, d_out);
 }
 
@@ -353,6 +358,7 @@ int b200zk_ntt_fr_dev(b200zk_ctx* ctx, int stream, const void* d_in, void* d_out
     if (!ctx || !valid_slot(stream) || !d_in || !d_out || batch == 0) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[stream];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     return ntt_dev(ctx, sl, reinterpret_cast<const Fr*>(d_in), reinterpret_cast<Fr*>(d_out), log_n, inverse != 0,
                    coset != 0, batch);
 }
@@ -362,6 +368,7 @@ int b200zk_ntt_fr_fourstep_cols_dev(b200zk_ctx* ctx, int stream, const void* d_i
     if (!ctx || !valid_slot(stream)) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[stream];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     return fourstep_cols_dev(ctx, sl, reinterpret_cast<const Fr*>(d_in), reinterpret_cast<Fr*>(d_out), log_rows,
                              log_cols_local, log_n, global_col0, inverse != 0);
 }
@@ -372,6 +379,7 @@ int b200zk_ntt_fr_fourstep_cols_p2p_dev(b200zk_ctx* ctx, int stream, const void*
     if (!ctx || !valid_slot(stream) || !d_in || !peer_out) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[stream];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     return fourstep_cols_p2p_dev(ctx, sl, reinterpret_cast<const Fr*>(d_in), peer_out, n_peers, log_rows, log_cols_local, log_n,
                                  global_col0, inverse != 0);
 }
@@ -381,6 +389,8 @@ int b200zk_peer_alloc(b200zk_ctx* ctx, size_t bytes, void** d_ptr, uint8_t handl
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
     B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     B2_CUDA_OK(ctx, cudaMalloc(d_ptr, bytes));
+    B2_CUDA_OK(ctx, cudaMemset(*d_ptr, 0, bytes));      // mailboxes (b200zk_msm_exchange_sum_dev) start with sequence flags = 0
+    B2_CUDA_OK(ctx, cudaDeviceSynchronize());
     cudaIpcMemHandle_t h;
     B2_CUDA_OK(ctx, cudaIpcGetMemHandle(&h, *d_ptr));
     memcpy(handle_out, &h, 64);
@@ -396,6 +406,7 @@ int b200zk_peer_open(b200zk_ctx* ctx, const uint8_t handle[64], void** d_ptr) {
 }
 int b200zk_peer_close(b200zk_ctx* ctx, void* d_ptr) {
     if (!ctx || !d_ptr) return B200ZK_ERR_ARG;
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     B2_CUDA_OK(ctx, cudaIpcCloseMemHandle(d_ptr));
     return B200ZK_OK;
 }
@@ -405,12 +416,22 @@ int b200zk_peer_free(b200zk_ctx* ctx, void* d_ptr) {
     return B200ZK_OK;
 }
 
+int b200zk_msm_exchange_sum_dev(b200zk_ctx* ctx, int stream, int g2, const void* d_partial, void* const* peer_mailboxes, unsigned n_peers,
+                                unsigned rank, uint64_t seq, void* d_out_affine) {
+    if (!ctx || !valid_slot(stream) || !d_partial || !peer_mailboxes || !d_out_affine) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[stream];
+    std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    return msm_exchange_sum_dev(ctx, sl, g2, d_partial, peer_mailboxes, n_peers, rank, seq, d_out_affine);
+}
+
 int b200zk_ntt_fr_batched_post_dev(b200zk_ctx* ctx, int stream, const void* d_in, void* d_out, unsigned log_t, unsigned batch,
                                    int inverse, unsigned log_base, int base_is_shift, uint64_t b0, uint64_t alpha,
                                    uint64_t beta, uint64_t gamma) {
     if (!ctx || !valid_slot(stream) || !d_in || !d_out || batch == 0) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[stream];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     return ntt_batched_post_dev(ctx, sl, reinterpret_cast<const Fr*>(d_in), reinterpret_cast<Fr*>(d_out), log_t, batch,
                                 inverse != 0, log_base, base_is_shift != 0, b0, alpha, beta, gamma);
 }
@@ -419,6 +440,7 @@ int b200zk_fr_mul_sub_dev(b200zk_ctx* ctx, int stream, const void* d_a, const vo
     if (!ctx || !valid_slot(stream) || (n && (!d_a || !d_b || !d_c || !d_out))) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[stream];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     return mul_sub_dev(ctx, sl, (const Fr*)d_a, (const Fr*)d_b, (const Fr*)d_c, (Fr*)d_out, n);
 }
 
@@ -427,6 +449,7 @@ int b200zk_h_circom_dev(b200zk_ctx* ctx, const void* d_a, const void* d_b, const
     if (!ctx || !d_a || !d_b || !d_c || !d_h) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[0];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     return h_circom_dev(ctx, sl, (const Fr*)d_a, (const Fr*)d_b, (const Fr*)d_c, log_m, (Fr*)d_h);
 }
 
@@ -455,12 +478,14 @@ int b200zk_qap_dev(b200zk_ctx* ctx, int stream, const void* a_ptr, const void* a
     if (!ctx || !valid_slot(stream) || !a_ptr || !b_ptr || !d_z || !d_a || !d_b || !d_c) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[stream];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     return qap_dev(ctx, sl, a_ptr, a_col, a_val, b_ptr, b_col, b_val, nc, n_inputs, d_z, log_m, d_a, d_b, d_c);
 }
 int b200zk_fr_convert_dev(b200zk_ctx* ctx, int stream, const void* d_in, void* d_out, size_t n, int to_mont, int times) {
     if (!ctx || !valid_slot(stream) || (n && (!d_in || !d_out)) || times < 0) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[stream];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     return fr_convert_dev(ctx, sl, d_in, d_out, n, to_mont, times);
 }
 
@@ -495,6 +520,7 @@ static int pk_build(b200zk_ctx* ctx, const void* a_query, const void* b_g1_query
     const char* env = getenv("B200ZK_PK_TABLES");
     if (!(env && env[0] == '0')) {
         std::lock_guard<std::mutex> g(ctx->slots[0].mu);
+        B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
         rc = pk_precompute_dev(ctx, pk, 0);
         if (rc) { b200zk_pk_free(ctx, pk); return rc; }
     }
@@ -528,6 +554,7 @@ int b200zk_pk_precompute(b200zk_ctx* ctx, b200zk_pk* pk, unsigned c) {
     if (!ctx || !pk) return B200ZK_ERR_ARG;
     B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));
     std::lock_guard<std::mutex> g(ctx->slots[0].mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     if (c == 0xFFFFFFFFu) { pk_free_tables(pk); return B200ZK_OK; }
     return pk_precompute_dev(ctx, pk, c);
 }
@@ -563,6 +590,7 @@ int b200zk_points_compress_dev(b200zk_ctx* ctx, int stream, int g2, const void* 
     if (!ctx || !valid_slot(stream) || (n && (!d_affine || !d_bytes))) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[stream];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     return points_compress_dev(ctx, sl, g2, d_affine, n, d_bytes);
 }
 int b200zk_points_decompress_dev(b200zk_ctx* ctx, int stream, int g2, const void* d_bytes, size_t n, int check_subgroup,
@@ -570,6 +598,7 @@ int b200zk_points_decompress_dev(b200zk_ctx* ctx, int stream, int g2, const void
     if (!ctx || !valid_slot(stream) || (n && (!d_affine || !d_bytes))) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[stream];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     return points_decompress_dev(ctx, sl, g2, d_bytes, n, check_subgroup, d_affine, n_invalid);
 }
 
@@ -578,6 +607,7 @@ int b200zk_points_matmul_dev(b200zk_ctx* ctx, int stream, int g2, const void* d_
     if (!ctx || !valid_slot(stream) || (n_chunks && rows && (!d_points || !d_matrix || !d_out))) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[stream];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     return points_matmul_dev(ctx, sl, g2, d_points, n_chunks, l, d_matrix, rows, d_out);
 }
 
@@ -598,6 +628,7 @@ int b200zk_xyzz_sum_dev(b200zk_ctx* ctx, int stream, int g2, const void* d_in, s
     if (!ctx || !valid_slot(stream) || !d_in || !d_out || count == 0) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[stream];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     return xyzz_sum_dev(ctx, sl, g2, d_in, count, stride, d_out);
 }
 int b200zk_groth16_assemble_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const void* d_msm_a, const void* d_msm_b2,
@@ -606,6 +637,7 @@ int b200zk_groth16_assemble_dev(b200zk_ctx* ctx, const b200zk_pk* pk, const void
     if (!ctx || !pk || !d_msm_a || !d_msm_b2 || !d_msm_l || !d_msm_h || !r || !s || !proof_out) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[0];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     return assemble_dev(ctx, sl, pk, d_msm_a, d_msm_b2, d_msm_l, d_msm_h, d_msm_b1, r, s, include_zero_terms, proof_out);
 }
 
@@ -621,6 +653,7 @@ int b200zk_fr_powers_dev(b200zk_ctx* ctx, const uint64_t base[4], const uint64_t
     if (!ctx || !base || !scale || (n && !d_out)) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[0];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     return fr_powers_dev(ctx, sl, base, scale, n, d_out);
 }
 int b200zk_fr_spmv_dev(b200zk_ctx* ctx, const void* d_ptr, const void* d_idx, const void* d_val, const void* d_x, size_t n_rows,
@@ -628,6 +661,7 @@ int b200zk_fr_spmv_dev(b200zk_ctx* ctx, const void* d_ptr, const void* d_idx, co
     if (!ctx || !d_ptr || !d_x || (n_rows && !d_out)) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[0];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     return spmv_dev(ctx, sl, d_ptr, d_idx, d_val, d_x, n_rows, d_out);
 }
 int b200zk_fr_lincomb_dev(b200zk_ctx* ctx, const void* d_a, const void* d_b, const void* d_c, const uint64_t s[16], size_t n,
@@ -635,6 +669,7 @@ int b200zk_fr_lincomb_dev(b200zk_ctx* ctx, const void* d_a, const void* d_b, con
     if (!ctx || !s || (n && (!d_a || !d_b || !d_c || !d_out))) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[0];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     return fr_lincomb_dev(ctx, sl, d_a, d_b, d_c, s, n, d_out);
 }
 
@@ -643,18 +678,21 @@ int b200zk_g1_generate_dev(b200zk_ctx* ctx, uint64_t seed, size_t n, void* d_out
     if (!ctx || (n && !d_out)) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[0];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     return generate_points_dev(ctx, sl, 0, seed, n, d_out);
 }
 int b200zk_g2_generate_dev(b200zk_ctx* ctx, uint64_t seed, size_t n, void* d_out) {
     if (!ctx || (n && !d_out)) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[0];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     return generate_points_dev(ctx, sl, 1, seed, n, d_out);
 }
 int b200zk_fr_generate_dev(b200zk_ctx* ctx, uint64_t seed, size_t n, void* d_out) {
     if (!ctx || (n && !d_out)) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[0];
     std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));     // the caller may have made another device current (multi-GPU groups)
     return generate_fr_dev(ctx, sl, seed, n, d_out);
 }
 

@@ -968,6 +968,80 @@ int g1_sum_dev(b200zk_ctx* ctx, Slot& sl, const void* d, size_t count, void* d_o
 int g2_sum_dev(b200zk_ctx* ctx, Slot& sl, const void* d, size_t count, void* d_out) { return sum_impl<Fq2>(ctx, sl, d, count, d_out); }
 
 // ---------------------------------------------------------------------------------------------
+// 8. d_msm's exchange as ONE kernel over peer memory (the king's gather + `unpackexp` + sum + scatter of
+//    dist-primitives/src/dmsm/mod.rs:87-97, and round 1's all-gather + host-synchronising sum): every rank stores its XYZZ
+//    partial into slot [parity][rank] of every peer's mailbox (NVLink stores), raises the slot's sequence flag, waits until
+//    all slots of its own mailbox carry this step's sequence number, adds the partials up and normalises.  No NCCL call, no
+//    host round trip; the two parities alternate so a fast peer's next partial never overwrites one still being read (a rank
+//    publishes step s + 1 only after its own sum of step s, and nobody can pass step s + 1 before everyone published it).
+//    Mailbox layout (bytes): [2][MAX_PEERS] slots of 256 B, then [2][MAX_PEERS] u64 flags.
+// ---------------------------------------------------------------------------------------------
+static const uint32_t XCH_MAX_PEERS = 8, XCH_SLOT = 256;
+struct PeerMailboxes { char* box[XCH_MAX_PEERS]; };
+
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <class F>
+__global__ void __launch_bounds__(32) k_msm_exchange_sum(const xyzz_t<F>* partial, PeerMailboxes peers, uint32_t n_peers, uint32_t rank,
+                                                         uint64_t seq, affine_t<F>* out, uint64_t* out_flag) {
+    const uint32_t par = (uint32_t)(seq & 1), lane = threadIdx.x;
+    constexpr uint32_t WORDS = sizeof(xyzz_t<F>) / 16;               // uint4 per partial: 8 (G1) or 16 (G2)
+    const uint4* src = reinterpret_cast<const uint4*>(partial);
+    // publish: lanes spread over (peer, 16-byte word); then one release-store of the flag per peer
+    for (uint32_t i = lane; i < n_peers * WORDS; i += 32) {
+        const uint32_t p = i / WORDS, w = i % WORDS;
+        reinterpret_cast<uint4*>(peers.box[p] + (size_t)(par * XCH_MAX_PEERS + rank) * XCH_SLOT)[w] = src[w];
+    }
+    __threadfence_system();
+    __syncwarp();
+    if (lane < n_peers) {
+        uint64_t* flags = reinterpret_cast<uint64_t*>(peers.box[lane] + 2 * XCH_MAX_PEERS * XCH_SLOT);
+        st_release_sys(flags + par * XCH_MAX_PEERS + rank, seq);
+    }
+    // wait for every rank's partial of this step in my own mailbox
+    char* mine = peers.box[rank];
+    const uint64_t* my_flags = reinterpret_cast<const uint64_t*>(mine + 2 * XCH_MAX_PEERS * XCH_SLOT);
+    if (lane < n_peers) {
+        while (ld_acquire_sys(my_flags + par * XCH_MAX_PEERS + lane) < seq) __nanosleep(200);
+    }
+    __syncwarp();
+    if (lane != 0) return;
+    xyzz_t<F> acc = xyzz_t<F>::identity();
+    for (uint32_t g = 0; g < n_peers; ++g) {
+        xyzz_t<F> v;
+        const volatile uint4* s4 = reinterpret_cast<const volatile uint4*>(mine + (size_t)(par * XCH_MAX_PEERS + g) * XCH_SLOT);
+        uint4* d4 = reinterpret_cast<uint4*>(&v);
+        for (uint32_t w = 0; w < WORDS; ++w) { uint4 t; t.x = s4[w].x; t.y = s4[w].y; t.z = s4[w].z; t.w = s4[w].w; d4[w] = t; }
+        acc = xyzz_t<F>::add(acc, v);
+    }
+    st16(out, xyzz_t<F>::to_affine(acc));
+    *out_flag = acc.is_inf() ? 1 : 0;
+}
+
+int msm_exchange_sum_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_partial, void* const* peer_boxes, unsigned n_peers, unsigned rank,
+                         uint64_t seq, void* d_out_affine) {
+    if (n_peers == 0 || n_peers > XCH_MAX_PEERS || rank >= n_peers || seq == 0) return set_error(ctx, B200ZK_ERR_ARG, "bad peer exchange geometry");
+    PeerMailboxes pm;
+    for (unsigned g = 0; g < XCH_MAX_PEERS; ++g) pm.box[g] = g < n_peers ? reinterpret_cast<char*>(peer_boxes[g]) : nullptr;
+    {
+        LaunchScope ls(ctx, sl.stream, "msm_exchange_sum");
+        if (g2) {
+            affine_t<Fq2>* o = reinterpret_cast<affine_t<Fq2>*>(d_out_affine);
+            k_msm_exchange_sum<Fq2><<<1, 32, 0, sl.stream>>>(reinterpret_cast<const xyzz_t<Fq2>*>(d_partial), pm, n_peers, rank, seq, o, reinterpret_cast<uint64_t*>(o + 1));
+        } else {
+            affine_t<Fq>* o = reinterpret_cast<affine_t<Fq>*>(d_out_affine);
+            k_msm_exchange_sum<Fq><<<1, 32, 0, sl.stream>>>(reinterpret_cast<const xyzz_t<Fq>*>(d_partial), pm, n_peers, rank, seq, o, reinterpret_cast<uint64_t*>(o + 1));
+        }
+    }
+    return check_launch(ctx, "k_msm_exchange_sum");
+}
+
+// ---------------------------------------------------------------------------------------------
 // deterministic dummy inputs + element-wise self-test
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {

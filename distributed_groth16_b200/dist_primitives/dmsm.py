@@ -55,12 +55,15 @@ def d_msm(bases, scalars, pp=None, net: Net | None = None, sid: MultiplexedStrea
     net.use_torch_stream(int(sid))
     part = net.msm_dev(bases, scalars, g2=g2, sid=int(sid))
     if net.n_parties() > 1:
-        import torch.distributed as dist
-        gathered = torch.empty((net.n_parties(), part.numel()), dtype=part.dtype, device=part.device)
-        dist.all_gather_into_tensor(gathered, part.reshape(1, -1))
-        limbs, inf = net.sum_points_dev(gathered, net.n_parties(), g2=g2, sid=int(sid))
-    else:
-        limbs, inf = net.sum_points_dev(part, 1, g2=g2, sid=int(sid))
+        # the star's gather / unpackexp / sum / scatter (dmsm/mod.rs:87-97) as one kernel over peer memory
+        xch = getattr(net, "_partial_exchange", None)
+        if xch is None:
+            from ..parallel import PartialExchange
+            xch = net._partial_exchange = PartialExchange(net)
+        res = xch.sum(part, g2=g2, sid=int(sid)).cpu().numpy().view(np.uint64)
+        w = 16 if g2 else 8
+        return GroupElement(res[:w].copy(), bool(res[w]), g2)
+    limbs, inf = net.sum_points_dev(part, 1, g2=g2, sid=int(sid))
     return GroupElement(limbs, inf, g2)
 
 

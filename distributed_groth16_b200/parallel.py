@@ -159,6 +159,61 @@ def sharded_msm(backend, bases, scalars, g2: bool = False, group=None):
     return backend.sum_points(gathered, world, g2)
 
 
+class PartialExchange:
+    """d_msm's exchange without NCCL: one mailbox per rank (b200zk_peer_alloc + CUDA IPC, opened by every peer once), then per
+    call ONE kernel per rank that stores its XYZZ partial into every peer's mailbox over NVLink, waits on sequence flags for
+    everybody's partial, adds them up and normalises (`b200zk_msm_exchange_sum_dev`).  Replaces send_to_king / unpackexp /
+    sum / recv_from_king of dist-primitives/src/dmsm/mod.rs:87-97 -- and round 1's all-gather + host-synchronising sum."""
+    MAILBOX_BYTES = 8192
+
+    def __init__(self, net, group=None):
+        import torch
+        import torch.distributed as dist
+        self.net, self.group = net, group
+        self.world, self.rank = _world(group)
+        lib, h = net._lib, net._h
+        ptr = c_vp()
+        hb = (ctypes.c_uint8 * 64)()
+        net.check(lib.b200zk_peer_alloc(h, self.MAILBOX_BYTES, ctypes.byref(ptr), hb))
+        self.local = ptr.value
+        self.boxes = [None] * self.world
+        self.boxes[self.rank] = self.local
+        if self.world > 1:
+            dev = torch.device("cuda", net.device)
+            mine = torch.tensor(list(bytes(hb)), dtype=torch.uint8, device=dev)
+            allh = torch.empty((self.world, 64), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, mine.reshape(1, -1), group=group)     # also orders every rank's zero-fill before first use
+            allh = allh.cpu().numpy()
+            for g in range(self.world):
+                if g != self.rank:
+                    raw = (ctypes.c_uint8 * 64).from_buffer_copy(allh[g].tobytes())
+                    p = c_vp()
+                    net.check(lib.b200zk_peer_open(h, raw, ctypes.byref(p)))
+                    self.boxes[g] = p.value
+        self._ptrs = (c_vp * self.world)(*[c_vp(p) for p in self.boxes])
+        self.seq = 0
+
+    def sum(self, part, g2: bool = False, out=None, sid: int = 0):
+        """part: this rank's XYZZ partial (CUDA int64 tensor).  Returns a CUDA tensor: affine limbs (8 / 16 words) + infinity flag,
+        identical on every rank; nothing is synchronised with the host."""
+        import torch
+        w = 16 if g2 else 8
+        if out is None:
+            out = torch.empty(w + 1, dtype=torch.int64, device=part.device)
+        self.seq += 1
+        net = self.net
+        net.check(net._lib.b200zk_msm_exchange_sum_dev(net._h, int(sid), 1 if g2 else 0, c_vp(part.data_ptr()), self._ptrs, self.world,
+                                                       self.rank, ctypes.c_uint64(self.seq), c_vp(out.data_ptr())))
+        return out
+
+    def close(self):
+        lib, h = self.net._lib, self.net._h
+        for g in range(self.world):
+            if g != self.rank and self.boxes[g]:
+                lib.b200zk_peer_close(h, c_vp(self.boxes[g]))
+        lib.b200zk_peer_free(h, c_vp(self.local))
+
+
 # ---------------------------------------------------------------------------------------------
 # multi-GPU prove (BASELINE config 5: MSM split + four-step NTT all-to-all)
 # ---------------------------------------------------------------------------------------------

@@ -121,6 +121,15 @@ int b200zk_peer_open(b200zk_ctx* ctx, const uint8_t handle[64], void** d_ptr);
 int b200zk_peer_close(b200zk_ctx* ctx, void* d_ptr);
 int b200zk_peer_free(b200zk_ctx* ctx, void* d_ptr);
 
+/* d_msm's exchange step as one kernel over peer memory (dmsm/mod.rs:87-97: send_to_king, unpackexp, sum, recv_from_king):
+ * every rank stores its XYZZ partial into every peer's mailbox, waits on sequence flags for the partials of all ranks, adds
+ * them and normalises -- no NCCL call, no host round trip.  peer_mailboxes[g]: rank g's mailbox (b200zk_peer_alloc of
+ * B200ZK_MAILBOX_BYTES, zero-filled; peers' opened with b200zk_peer_open).  seq: 1, 2, 3, ... the same on every rank.
+ * d_out_affine: 64 / 128 bytes of canonical affine coordinates followed by one u64 infinity flag. */
+#define B200ZK_MAILBOX_BYTES 8192
+int b200zk_msm_exchange_sum_dev(b200zk_ctx* ctx, int stream, int g2, const void* d_partial, void* const* peer_mailboxes,
+                                unsigned n_peers, unsigned rank, uint64_t seq, void* d_out_affine);
+
 /* Generalised building block: `batch` contiguous transforms of size 2^log_t; output k of transform b is
  * multiplied by base^((b + b0)(alpha k + beta) + gamma k) where base = w_{2^log_base} (direction of the
  * transform) or, with base_is_shift, the forward root w_{2^log_base} used by the h coefficient shift.
