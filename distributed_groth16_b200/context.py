@@ -201,8 +201,22 @@ class Net:
     def field_op(self, field: int, op: int, a, b):
         a, b = _as_u64(a, 4), _as_u64(b, 4)
         out = np.zeros_like(a)
-        self.check(self._lib.b200zk_test_field_op(self._h, field, op, _ptr(a), _ptr(b), _ptr(out), a.shape[0]))
+        if field == 1:        # Fr: the documented share-arithmetic entry point; Fq exists for the self-tests only
+            self.check(self._lib.b200zk_fr_op(self._h, op, _ptr(a), _ptr(b), _ptr(out), a.shape[0]))
+        else:
+            self.check(self._lib.b200zk_test_field_op(self._h, field, op, _ptr(a), _ptr(b), _ptr(out), a.shape[0]))
         return out
+
+    def fr_powers(self, base: int, scale: int, n: int) -> np.ndarray:
+        """scale * base^i, i < n, as (n, 4) Montgomery limbs -- computed on the device (b200zk_fr_powers_dev): the twiddle
+        columns of the n-party fft1 / fft2 stages (dfft/mod.rs:124-134 walks `factor *= factor_stride` serially)."""
+        import torch
+        R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
+        mont = lambda v: np.array([(((int(v) % R) << 256) % R >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+        out = torch.empty((n, 4), dtype=torch.int64, device=self._dev())
+        b, s = mont(base), mont(scale)
+        self.check(self._lib.b200zk_fr_powers_dev(self._h, c_vp(b.ctypes.data), c_vp(s.ctypes.data), n, c_vp(out.data_ptr())))
+        return out.cpu().numpy().view(np.uint64)
 
     # -- device-resident (torch tensors, int64 view of the u64 limbs) -----------------------------
     def _dev(self):

@@ -696,6 +696,11 @@ int b200zk_fr_generate_dev(b200zk_ctx* ctx, uint64_t seed, size_t n, void* d_out
     return generate_fr_dev(ctx, sl, seed, n, d_out);
 }
 
+int b200zk_fr_op(b200zk_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+    if (op < 0 || op > 2) return B200ZK_ERR_ARG;
+    return b200zk_test_field_op(ctx, 1, op, a, b, out, n);
+}
+
 int b200zk_test_field_op(b200zk_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
     if (!ctx || !a || !b || !out) return B200ZK_ERR_ARG;
     Slot& sl = ctx->slots[0];

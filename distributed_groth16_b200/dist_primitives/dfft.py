@@ -98,7 +98,7 @@ def _fft1_in_place(px: np.ndarray, dom_size: int, l: int, gen: int, net) -> np.n
         ps = dom_size >> i
         stride = pow(gen, 1 << (i - 1), _FR)
         nj = (1 << (i - 1)) // l
-        f = _mont_limbs([pow(stride, k + 1, _FR) for k in range(ps)])
+        f = net.fr_powers(stride, stride, ps)                    # stride^(k+1), k < ps
         v = px.reshape(nj, 2, ps, 4)
         x = np.ascontiguousarray(v[:, 0]).reshape(-1, 4)
         y = np.ascontiguousarray(v[:, 1]).reshape(-1, 4)
@@ -115,7 +115,7 @@ def _fft2_in_place(s1: np.ndarray, dom_size: int, l: int, gen: int, net) -> np.n
         ps = dom_size >> i
         stride = pow(gen, 1 << (i - 1), _FR)
         half = 1 << (i - 1)
-        f = _mont_limbs([pow(stride, k + 1, _FR) for k in range(ps)])
+        f = net.fr_powers(stride, stride, ps)
         v = s1.reshape(ps, half, 2, 4)                           # s1[k * 2^i + 2j + b]
         x = np.ascontiguousarray(v[:, :, 0]).reshape(-1, 4)
         y = np.ascontiguousarray(v[:, :, 1]).reshape(-1, 4)

@@ -280,6 +280,12 @@ int b200zk_group_groth16_prove(b200zk_group* group, const b200zk_group_pk* pk, c
                                const uint64_t* b, const uint64_t* c, const uint64_t r[4], const uint64_t s[4],
                                uint8_t proof_out[128]);
 
+/* ---- the parties' local share arithmetic (n-party compatibility mirrors) ----------------------------------
+ * Element-wise Fr operation on host buffers of n x 4 Montgomery limbs: op 0 = a * b (share-wise product of two sharings,
+ * e.g. the degree-2 input of d_fft, dfft/mod.rs:207-211), 1 = a + b, 2 = a - b (with 0 the butterflies of fft1_in_place,
+ * dfft/mod.rs:122-135, one call per stage for all of a party's butterflies). */
+int b200zk_fr_op(b200zk_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
+
 /* ---- self-test hooks (tests only): element-wise field ops on device ------------------------- */
 /* op: 0 mul, 1 add, 2 sub; field: 0 Fq, 1 Fr.  a, b, out: n x 4 limbs host buffers. */
 int b200zk_test_field_op(b200zk_ctx* ctx, int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out,

@@ -20,6 +20,10 @@ class OracleNet:
         f = (lambda p, q: p * q % o.R, lambda p, q: (p + q) % o.R, lambda p, q: (p - q) % o.R)[op]
         return layout.fr_to_arr([f(p, q) for p, q in zip(x, y)])
 
+    def fr_powers(self, base, scale, n):
+        from oracle import bn254 as o, layout
+        return layout.fr_to_arr([scale * pow(base, i, o.R) % o.R for i in range(n)])
+
     def ntt(self, data, inverse=False, coset=False, **_):
         from oracle import bn254 as o, layout
         v = layout.arr_to_fr(np.asarray(data).reshape(-1, 4))
