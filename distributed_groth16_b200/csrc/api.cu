@@ -46,7 +46,7 @@ int b200zk_ctx_create(int device, b200zk_ctx** out) {
                   cudaStreamCreateWithFlags(&ctx->slots[i].aux_stream, cudaStreamNonBlocking) == cudaSuccess &&
                   cudaEventCreateWithFlags(&ctx->slots[i].copy_done, cudaEventDisableTiming) == cudaSuccess &&
                   cudaEventCreateWithFlags(&ctx->slots[i].aux_done, cudaEventDisableTiming) == cudaSuccess;
-        for (int k = 0; ok && k < 4; ++k) ok = cudaEventCreateWithFlags(&ctx->slots[i].stage_ev[k], cudaEventDisableTiming) == cudaSuccess;
+        for (int k = 0; ok && k < 32; ++k) ok = cudaEventCreateWithFlags(&ctx->slots[i].stage_ev[k], cudaEventDisableTiming) == cudaSuccess;
         if (!ok) {
             delete ctx;
             return B200ZK_ERR_CUDA;
@@ -88,7 +88,7 @@ void b200zk_ctx_destroy(b200zk_ctx* ctx) {
         if (s.aux_stream) cudaStreamDestroy(s.aux_stream);
         if (s.copy_done) cudaEventDestroy(s.copy_done);
         if (s.aux_done) cudaEventDestroy(s.aux_done);
-        for (int k = 0; k < 4; ++k) if (s.stage_ev[k]) cudaEventDestroy(s.stage_ev[k]);
+        for (int k = 0; k < 32; ++k) if (s.stage_ev[k]) cudaEventDestroy(s.stage_ev[k]);
     }
     if (ctx->hi_stream) cudaStreamDestroy(ctx->hi_stream);
     for (int k = 0; k < 6; ++k) if (ctx->msm_side[k]) cudaStreamDestroy(ctx->msm_side[k]);
@@ -214,29 +214,39 @@ static int msm_host(b200zk_ctx* ctx, int stream, const uint64_t* bases, size_t n
     B2_CUDA_OK(ctx, sl.small.reserve(1024));
     char* d_bases = reinterpret_cast<char*>(sl.io_a.p);
     char* d_scalars = d_bases + n * PB;
-    static const bool split_env = !(getenv("B200ZK_MSM_SPLIT") && getenv("B200ZK_MSM_SPLIT")[0] == '0');
-    if (!G2 && split_env && n >= ((size_t)1 << 18)) {
-        // two halves, two compute streams: H2D order scalars-1, bases-1, scalars-2, bases-2 on the copy stream
-        const size_t n1 = n / 2, n2 = n - n1;
+    // Large inputs travel in parts on the copy stream (scalars of part p, bases of part p, scalars of part p + 1, ...): the sort
+    // phases of a part start when its scalars are there, its bucket kernel when its bases are, and every part adds into the
+    // same bucket set -- the PCIe transfer of part p + 1 hides behind the bucket kernel of part p (msm.cu, msm_dev_impl).
+    static const int parts_env = getenv("B200ZK_MSM_PARTS") ? atoi(getenv("B200ZK_MSM_PARTS")) : 0;
+    unsigned nparts = parts_env > 0 ? (unsigned)parts_env : (n >= ((size_t)1 << 18) ? 4u : 1u);
+    if (nparts > 16) nparts = 16;
+    if (nparts > 1) {
         const char* hb = reinterpret_cast<const char*>(bases);
         const char* hs = reinterpret_cast<const char*>(scalars);
         cudaStream_t cs = sl.copy_stream;
-        B2_CUDA_OK(ctx, cudaMemcpyAsync(d_scalars, hs, n1 * 32, cudaMemcpyHostToDevice, cs));
-        B2_CUDA_OK(ctx, cudaEventRecord(sl.stage_ev[0], cs));
-        B2_CUDA_OK(ctx, cudaMemcpyAsync(d_bases, hb, n1 * PB, cudaMemcpyHostToDevice, cs));
-        B2_CUDA_OK(ctx, cudaEventRecord(sl.stage_ev[1], cs));
-        B2_CUDA_OK(ctx, cudaMemcpyAsync(d_scalars + n1 * 32, hs + n1 * 32, n2 * 32, cudaMemcpyHostToDevice, cs));
-        B2_CUDA_OK(ctx, cudaEventRecord(sl.stage_ev[2], cs));
-        B2_CUDA_OK(ctx, cudaMemcpyAsync(d_bases + n1 * PB, hb + n1 * PB, n2 * PB, cudaMemcpyHostToDevice, cs));
-        B2_CUDA_OK(ctx, cudaEventRecord(sl.stage_ev[3], cs));
-        char* sm2 = reinterpret_cast<char*>(sl.small.p);
-        B2_TRY(msm_g1_two_halves_dev(ctx, sl, d_bases, d_scalars, n1, n2, sl.stage_ev, sm2));
-        B2_TRY(g1_sum_dev(ctx, sl, sm2, 2, sm2 + 256));
-        uint64_t host2[9];
-        B2_CUDA_OK(ctx, cudaMemcpyAsync(host2, sm2 + 256, PB + 8, cudaMemcpyDeviceToHost, sl.stream));
+        size_t cnt[16];
+        cudaEvent_t ev_s[16], ev_b[16];
+        size_t lo = 0;
+        for (unsigned p = 0; p < nparts; ++p) {
+            const size_t hi = (size_t)(((unsigned __int128)n * (p + 1)) / nparts);
+            cnt[p] = hi - lo;
+            B2_CUDA_OK(ctx, cudaMemcpyAsync(d_scalars + lo * 32, hs + lo * 32, cnt[p] * 32, cudaMemcpyHostToDevice, cs));
+            B2_CUDA_OK(ctx, cudaEventRecord(sl.stage_ev[2 * p], cs));
+            B2_CUDA_OK(ctx, cudaMemcpyAsync(d_bases + lo * PB, hb + lo * PB, cnt[p] * PB, cudaMemcpyHostToDevice, cs));
+            B2_CUDA_OK(ctx, cudaEventRecord(sl.stage_ev[2 * p + 1], cs));
+            ev_s[p] = sl.stage_ev[2 * p];
+            ev_b[p] = sl.stage_ev[2 * p + 1];
+            lo = hi;
+        }
+        char* sm = reinterpret_cast<char*>(sl.small.p);
+        B2_TRY(msm_parts_dev(ctx, sl, G2, d_bases, d_scalars, cnt, nparts, ev_s, ev_b, sm));
+        B2_TRY(G2 ? g2_sum_dev(ctx, sl, sm, 1, sm + XB) : g1_sum_dev(ctx, sl, sm, 1, sm + XB));
+        uint64_t hostp[17];
+        B2_CUDA_OK(ctx, cudaMemcpyAsync(hostp, sm + XB, PB + 8, cudaMemcpyDeviceToHost, sl.stream));
         B2_CUDA_OK(ctx, cudaStreamSynchronize(sl.stream));
-        memcpy(out_affine, host2, PB);
-        *out_is_inf = (int)host2[PB / 8];
+        B2_CUDA_OK(ctx, cudaStreamSynchronize(cs));
+        memcpy(out_affine, hostp, PB);
+        *out_is_inf = (int)hostp[PB / 8];
         return B200ZK_OK;
     }
     if (n) {

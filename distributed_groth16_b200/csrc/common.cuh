@@ -52,7 +52,8 @@ struct Slot {                 // one per MultiplexedStreamID
     cudaEvent_t copy_done = nullptr;
     cudaStream_t aux_stream = nullptr;    // second compute stream + workspace: host-staged MSMs run as two halves
     DevBuf ws_msm_aux;
-    cudaEvent_t aux_done = nullptr, stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t aux_done = nullptr;
+    cudaEvent_t stage_ev[32] = {};        // host-staged MSM: arrival of part p's scalars [2 p] / bases [2 p + 1]
 };
 
 }  // namespace b200zk
@@ -200,8 +201,8 @@ int msm_g1_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_sca
                cudaEvent_t bases_ready = nullptr, int aux = 0);
 int msm_g2_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n, void* d_out_xyzz,
                cudaEvent_t bases_ready = nullptr, int aux = 0);
-int msm_g1_two_halves_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n1, size_t n2,
-                          cudaEvent_t ev[4], void* d_out2);
+int msm_parts_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_bases, const void* d_scalars, const size_t* cnt, unsigned nparts,
+                  const cudaEvent_t* ev_scalars, const cudaEvent_t* ev_bases, void* d_out_xyzz);
 unsigned msm_table_windows(unsigned c);
 unsigned msm_table_auto_window(size_t n);
 int msm_table_build_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_bases, size_t n, unsigned c, void* d_table);

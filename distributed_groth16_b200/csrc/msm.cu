@@ -278,7 +278,7 @@ __global__ void k_msm_task_order(const uint32_t* offsets, const uint32_t* task_o
 template <class F>
 __global__ void __launch_bounds__(128, sizeof(F) > 32 ? B2_ACC_MINBLOCKS_G2 : B2_ACC_MINBLOCKS) k_msm_accumulate(const affine_t<F>* bases, const uint32_t* entries, const uint32_t* offsets,
                                  const uint32_t* task_off, const uint32_t* task_bucket, const uint32_t* order,
-                                 uint32_t nbuckets, uint32_t task_len, uint32_t wave, xyzz_t<F>* buckets, xyzz_t<F>* task_sums) {
+                                 uint32_t nbuckets, uint32_t task_len, uint32_t wave, uint32_t rmw, xyzz_t<F>* buckets, xyzz_t<F>* task_sums) {
     // Block order over the length-sorted task list: the first `wave` blocks (one per resident slot) take an evenly
     // strided sample of the list, i.e. every length from the longest to the shortest, the others follow in descending
     // order.  In plain descending order each generation of resident blocks has equal lengths and ends at the same
@@ -304,7 +304,9 @@ __global__ void __launch_bounds__(128, sizeof(F) > 32 ? B2_ACC_MINBLOCKS_G2 : B2
     uint32_t t0 = task_off[g], nt = task_off[g + 1] - t0;
     uint32_t lo = offsets[g] + (t - t0) * task_len, end = offsets[g + 1];
     uint32_t hi = lo + task_len < end ? lo + task_len : end;
+    // rmw (several input parts, msm_dev_impl): a single-task bucket continues from what the earlier parts left in it
     xyzz_t<F> acc = xyzz_t<F>::identity();
+    if (rmw && nt == 1) acc = ld16(buckets + g);
     for (uint32_t k = lo; k < hi; ++k) {
         uint32_t e = entries[k];
         affine_t<F> p = ld16(bases + (e & 0x7FFFFFFFu));
@@ -323,7 +325,7 @@ __device__ __forceinline__ xyzz_t<F> add_sel(const xyzz_t<F>& a, const xyzz_t<F>
 // buckets[g] = sum of the task sums of g, for every multi-task bucket; one block per bucket, grid-strided
 template <class F>
 __global__ void __launch_bounds__(128) k_msm_merge_tasks(const uint32_t* multi_list, const uint32_t* multi_count,
-                                  const uint32_t* task_off, const xyzz_t<F>* task_sums, xyzz_t<F>* buckets) {
+                                  const uint32_t* task_off, const xyzz_t<F>* task_sums, uint32_t rmw, xyzz_t<F>* buckets) {
     __shared__ xyzz_t<F> sh[128];
     uint32_t cnt = *multi_count;
     for (uint32_t i = blockIdx.x; i < cnt; i += gridDim.x) {
@@ -340,7 +342,7 @@ __global__ void __launch_bounds__(128) k_msm_merge_tasks(const uint32_t* multi_l
             }
             __syncthreads();
         }
-        if (threadIdx.x == 0) st16(buckets + g, sh[0]);
+        if (threadIdx.x == 0) st16(buckets + g, rmw ? add_sel<F>(ld16(buckets + g), sh[0]) : sh[0]);
         __syncthreads();
     }
 }
@@ -348,13 +350,14 @@ __global__ void __launch_bounds__(128) k_msm_merge_tasks(const uint32_t* multi_l
 // the buckets with 2..MERGE_SMALL tasks (n >> 2^c: most of them): one thread per bucket
 template <class F>
 __global__ void __launch_bounds__(128) k_msm_merge_small(const uint32_t* multi_list, uint32_t list_cap, const uint32_t* small_count,
-                                                         const uint32_t* task_off, const xyzz_t<F>* task_sums, xyzz_t<F>* buckets) {
+                                                         const uint32_t* task_off, const xyzz_t<F>* task_sums, uint32_t rmw, xyzz_t<F>* buckets) {
     uint32_t cnt = *small_count;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
         uint32_t g = multi_list[list_cap - 1 - i];
         uint32_t lo = task_off[g], hi = task_off[g + 1];
         xyzz_t<F> acc = ld16(task_sums + lo);
         for (uint32_t t = lo + 1; t < hi; ++t) acc = add_sel<F>(acc, ld16(task_sums + t));
+        if (rmw) acc = add_sel<F>(ld16(buckets + g), acc);
         st16(buckets + g, acc);
     }
 }
@@ -544,10 +547,31 @@ struct MsmStreams {
 // point operations that used to follow the bucket kernel (1.0 of 4.0 ms at 2^20) -- overlaps accumulate(g + 1); only
 // the last group's tail is exposed.  `seq` has the higher stream priority: its short kernels get the SM slots that
 // the running bucket kernel frees, instead of queueing behind it.
+// One input part of an MSM: `n` pairs, and (host-staged callers) the events that signal the arrival of its scalars / bases.
+struct MsmPart {
+    const void* bases;
+    const void* scalars;
+    size_t n;
+    cudaEvent_t bases_ready, scalars_ready;
+};
+
+// The window-group pipeline (one MSM, no host round trips):
+//   seq : digits, scan | prep(0) | prep(1) .. prep(G-1) | wait A0: tail(0) | wait A1: tail(1) | ...
+//   acc :                 wait P0: accumulate(0) -> A0 | wait P1: accumulate(1) -> A1 | ...
+// prep(g) = task tables + scatter of group g's bucket sets, tail(g) = merge + bucket reduction + window sums + Horner
+// step.  Groups hold consecutive bucket sets in Horner order (top windows first), so tail(g) -- a chain of dependent
+// point operations that used to follow the bucket kernel (1.0 of 4.0 ms at 2^20) -- overlaps accumulate(g + 1); only
+// the last group's tail is exposed.  `seq` has the higher stream priority: its short kernels get the SM slots that
+// the running bucket kernel frees, instead of queueing behind it.
+//
+// Several input PARTS (host-staged MSMs, api.cu): the pairs arrive over PCIe in `nparts` pieces.  Every part is sorted on
+// its own (digits / scan / task tables / scatter on seq as soon as its scalars are there) and its bucket kernel ADDS into
+// the one shared bucket set as soon as its bases are there (read-modify-write of the XYZZ buckets), so the transfer of
+// part p + 1 hides behind the bucket kernel of part p and the reduction / Horner tail runs once.  (Round 1 ran two
+// complete MSMs on two streams instead: two bucket sets, two tails, 5.2 ms end to end at 2^20 against 4.0 ms resident.)
 template <class F>
-static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, const void* d_bases, const void* d_scalars, size_t n,
-                        void* d_out, const char* acc_name, cudaEvent_t bases_ready, cudaEvent_t scalars_ready = nullptr,
-                        unsigned tab_c = 0, unsigned c_force = 0) {
+static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, const MsmPart* parts, unsigned nparts,
+                        void* d_out, const char* acc_name, unsigned tab_c = 0, unsigned c_force = 0) {
     const cudaStream_t st = ms.seq, ast = ms.acc;
     const int ch = ms.channel;
     size_t nev = 0;
@@ -568,7 +592,8 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
         }
         return B200ZK_OK;
     };
-    if (scalars_ready) B2_CUDA_OK(ctx, cudaStreamWaitEvent(st, scalars_ready, 0));
+    size_t n = 0, n_max = 0;                                 // all parts together / the largest part
+    for (unsigned p = 0; p < nparts; ++p) { n += parts[p].n; n_max = parts[p].n > n_max ? parts[p].n : n_max; }
     xyzz_t<F>* out = reinterpret_cast<xyzz_t<F>*>(d_out);
     if (n == 0) {
         {
@@ -579,9 +604,10 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
         return finish();
     }
     if (n >= (1ull << 31)) return set_error(ctx, B200ZK_ERR_ARG, "MSM length must be < 2^31");
-    // tab_c != 0: d_bases is a fixed-base table of msm_table_windows(tab_c) x n points (section 7); all digit windows
+    // tab_c != 0: the bases are a fixed-base table of msm_table_windows(tab_c) x n points (section 7); all digit windows
     // then share one bucket set and the Horner chain disappears
     const bool fold = tab_c != 0;
+    if (fold && nparts != 1) return set_error(ctx, B200ZK_ERR_ARG, "fixed-base tables take one input part");
     const unsigned c = fold ? tab_c : (c_force ? c_force : choose_window(n));
     static const bool glv_env = !(getenv("B200ZK_MSM_GLV") && getenv("B200ZK_MSM_GLV")[0] == '0');
     const bool glv = !fold && glv_env && sizeof(F) == 32;    // G1 only (glv.cuh)
@@ -600,14 +626,14 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
     }
     const uint32_t nseg = B / seg_len;
     const uint32_t wsplit = (fold && nseg >= 16 * 256) ? 16 : 1;
-    const size_t total = (size_t)W * n;
 
     // window groups: consecutive bucket sets (GLV: whole windows, i.e. both halves).  Measured (profiles/r2_msm_groups.md):
     // at 2^20 the extra launches, the drain bubble at the end of every bucket kernel and the slowdown of the latency-bound
     // tail kernels when they share SMs with a bucket kernel cost more than the hidden tail saves (3.94 ms with 1 group,
-    // 4.44 with 2, 5.06 with 4); from 2^22 up four groups win (15.63 -> 14.41 ms).  Fixed-base tables have one bucket set.
+    // 4.44 with 2, 5.06 with 4); from 2^22 up four groups win (15.63 -> 14.41 ms).  Fixed-base tables have one bucket set;
+    // several input parts already cut the bucket work into pieces.
     unsigned ngroups = 1;
-    if (!fold) {
+    if (!fold && nparts == 1) {
         static const int g_env = getenv("B200ZK_MSM_GROUPS") ? atoi(getenv("B200ZK_MSM_GROUPS")) : 0;
         const unsigned nunits = glv ? Wh : W;                // windows
         unsigned want = g_env > 0 ? (unsigned)g_env : (n >= (1u << 22) ? 4u : 1u);
@@ -617,75 +643,60 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
     const unsigned unit_sets = glv ? 2 : 1;
     const unsigned units = (fold ? 1 : (glv ? Wh : W));
     auto group_first_unit = [&](unsigned g) { return (unsigned)(((uint64_t)units * g) / ngroups); };   // balanced split
+    const uint32_t rmw = nparts > 1 ? 1u : 0u;               // bucket kernels add into the shared buckets
 
-    // workspace carve-up (256-byte aligned)
+    // workspace carve-up (256-byte aligned): the sort arrays once per part, the bucket set and the reduction buffers once
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
     // task length: 128 unless the average bucket is already that long (n >> 2^c: every bucket would be cut in two);
     // then the next power of two above 3x the average -- only outliers are split -- as long as that leaves enough
     // tasks (>= 2^19) to fill the machine
+    const size_t total_max = (size_t)W * n_max;
     uint32_t task_len = TASK_LEN;
-    while (task_len < MAX_TASK_LEN && (uint64_t)task_len * nb < 3 * (uint64_t)total &&
-           total / (2 * task_len) + nb >= (1u << 19))
+    while (task_len < MAX_TASK_LEN && (uint64_t)task_len * nb < 3 * (uint64_t)total_max &&
+           total_max / (2 * task_len) + nb >= (1u << 19))
         task_len *= 2;
-    const size_t max_tasks = total / task_len + nb + ngroups;                 // all groups together
+    const size_t max_tasks = total_max / task_len + nb + ngroups;             // per part, all groups together
     size_t o = 0;
     auto carve = [&](size_t bytes) { size_t r = o; o += al(bytes); return r; };
-    const size_t o_keys = carve(total * 4), o_ranks = carve(total * 4), o_entries = carve(total * 4);
-    const size_t o_counts = carve(((size_t)nb + 1) * 4), o_offsets = carve(((size_t)nb + 1) * 4);
+    struct PartWs { size_t keys, ranks, entries, counts, offsets, ntasks, taskoff, taskbucket, multi, hist, rank, order, tasksums; };
+    std::vector<PartWs> pw(nparts);
+    for (unsigned p = 0; p < nparts; ++p) {
+        const size_t total = (size_t)W * parts[p].n;
+        pw[p].keys = carve(total * 4); pw[p].ranks = carve(total * 4); pw[p].entries = carve(total * 4);
+        pw[p].counts = carve(((size_t)nb + 1) * 4); pw[p].offsets = carve(((size_t)nb + 1) * 4);
+        pw[p].ntasks = carve(((size_t)nb + ngroups) * 4); pw[p].taskoff = carve(((size_t)nb + ngroups) * 4);
+        pw[p].taskbucket = carve(max_tasks * 4);
+        pw[p].multi = carve((total_max / task_len + 4 * ngroups + 4) * 4);
+        pw[p].hist = carve((size_t)ngroups * (MAX_TASK_LEN + 1) * 4);
+        pw[p].rank = carve(max_tasks * 4); pw[p].order = carve(max_tasks * 4);
+        pw[p].tasksums = carve(max_tasks * sizeof(xyzz_t<F>));
+    }
     const size_t o_sums = carve(((size_t)nb / SCAN_TILE + 2) * 4);
-    const size_t o_ntasks = carve(((size_t)nb + ngroups) * 4), o_taskoff = carve(((size_t)nb + ngroups) * 4);
-    const size_t o_taskbucket = carve(max_tasks * 4);
-    const size_t o_multi = carve((total / task_len + 4 * ngroups + 4) * 4);
-    const size_t o_hist = carve((size_t)ngroups * (MAX_TASK_LEN + 1) * 4);
-    const size_t o_rank = carve(max_tasks * 4), o_order = carve(max_tasks * 4);
-    const size_t o_tasksums = carve(max_tasks * sizeof(xyzz_t<F>));
     const size_t o_buckets = carve((size_t)nb * sizeof(xyzz_t<F>));
     const size_t o_partials = carve((size_t)WB * nseg * sizeof(xyzz_t<F>));
     const size_t o_wsum = carve((size_t)WB * wsplit * sizeof(xyzz_t<F>));
     const size_t o_state = carve(2 * sizeof(xyzz_t<F>));
     B2_CUDA_OK(ctx, ws_buf.reserve(o));
     char* ws = reinterpret_cast<char*>(ws_buf.p);
-    uint32_t* keys = reinterpret_cast<uint32_t*>(ws + o_keys);
-    uint32_t* ranks = reinterpret_cast<uint32_t*>(ws + o_ranks);
-    uint32_t* entries = reinterpret_cast<uint32_t*>(ws + o_entries);
-    uint32_t* counts = reinterpret_cast<uint32_t*>(ws + o_counts);
-    uint32_t* offsets = reinterpret_cast<uint32_t*>(ws + o_offsets);
     uint32_t* sums = reinterpret_cast<uint32_t*>(ws + o_sums);
-    uint32_t* ntasks_all = reinterpret_cast<uint32_t*>(ws + o_ntasks);
-    uint32_t* task_off_all = reinterpret_cast<uint32_t*>(ws + o_taskoff);
-    uint32_t* task_bucket_all = reinterpret_cast<uint32_t*>(ws + o_taskbucket);
-    uint32_t* multi_all = reinterpret_cast<uint32_t*>(ws + o_multi);
-    uint32_t* hist_all = reinterpret_cast<uint32_t*>(ws + o_hist);
-    uint32_t* task_rank_all = reinterpret_cast<uint32_t*>(ws + o_rank);
-    uint32_t* order_all = reinterpret_cast<uint32_t*>(ws + o_order);
-    xyzz_t<F>* task_sums_all = reinterpret_cast<xyzz_t<F>*>(ws + o_tasksums);
     xyzz_t<F>* buckets = reinterpret_cast<xyzz_t<F>*>(ws + o_buckets);
     xyzz_t<F>* partials = reinterpret_cast<xyzz_t<F>*>(ws + o_partials);
     xyzz_t<F>* wsum = reinterpret_cast<xyzz_t<F>*>(ws + o_wsum);
     xyzz_t<F>* hstate = reinterpret_cast<xyzz_t<F>*>(ws + o_state);
-
-    B2_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, ((size_t)nb + 1) * 4, st));
-    {
-        LaunchScope ls(ctx, st, "msm_digits");
-        if (glv) k_msm_digits_glv<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const Fr*>(d_scalars), (uint32_t)n, c,
-                                                                              Wh, keys, ranks, counts);
-        else k_msm_digits<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const Fr*>(d_scalars), (uint32_t)n, c, W,
-                                                                         fold ? 1u : 0u, keys, ranks, counts);
-    }
-    B2_TRY(check_launch(ctx, "k_msm_digits"));
-    B2_TRY(exclusive_scan(ctx, st, counts, offsets, sums, nb + 1));
-    B2_CUDA_OK(ctx, cudaMemsetAsync(multi_all, 0, (size_t)ngroups * 8, st));          // [2 g], [2 g + 1] = big / small counts
-    B2_CUDA_OK(ctx, cudaMemsetAsync(hist_all, 0, (size_t)ngroups * (MAX_TASK_LEN + 1) * 4, st));
     B2_CUDA_OK(ctx, cudaMemsetAsync(buckets, 0, (size_t)nb * sizeof(xyzz_t<F>), st));   // all-zero XYZZ = identity
+    cudaEvent_t buckets_clear = nullptr;
+    if (rmw) {                                               // the first bucket kernel reads the buckets it adds into
+        buckets_clear = next_event();
+        if (!buckets_clear) return set_error(ctx, B200ZK_ERR_CUDA, "cudaEventCreate failed");
+        B2_CUDA_OK(ctx, cudaEventRecord(buckets_clear, st));
+        B2_CUDA_OK(ctx, cudaStreamWaitEvent(ast, buckets_clear, 0));
+    }
 
-    if (bases_ready) B2_CUDA_OK(ctx, cudaStreamWaitEvent(ast, bases_ready, 0));
-
-    // per-group views of the task tables
+    // per-group views of the task tables (same geometry for every part)
     struct Group {
         uint32_t set0, nsets, b0, nbk;          // bucket sets [set0, set0 + nsets), buckets [b0, b0 + nbk)
         size_t task_cap, task_base;             // task arrays: [task_base, task_base + task_cap)
         uint32_t list_cap; size_t list_base;    // multi-task bucket list
-        cudaEvent_t prepped, accumulated;
     };
     std::vector<Group> groups(ngroups);
     {
@@ -695,69 +706,24 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
             const unsigned u0 = group_first_unit(g), u1 = group_first_unit(g + 1);
             G.set0 = u0 * unit_sets; G.nsets = (u1 - u0) * unit_sets;
             G.b0 = G.set0 * B; G.nbk = G.nsets * B;
-            const size_t gtotal = fold ? total : (size_t)G.nsets * n;
+            const size_t gtotal = fold ? total_max : (size_t)G.nsets * n_max;
             G.task_cap = gtotal / task_len + G.nbk + 1;
             G.task_base = tb; tb += G.task_cap;
             G.list_cap = (uint32_t)(gtotal / task_len + 1);
             G.list_base = lb; lb += G.list_cap;
-            G.prepped = next_event(); G.accumulated = next_event();
-            if (!G.prepped || !G.accumulated) return set_error(ctx, B200ZK_ERR_CUDA, "cudaEventCreate failed");
         }
     }
+    std::vector<cudaEvent_t> prepped((size_t)nparts * ngroups), accumulated((size_t)nparts * ngroups);
+    for (auto& e : prepped) if (!(e = next_event())) return set_error(ctx, B200ZK_ERR_CUDA, "cudaEventCreate failed");
+    for (auto& e : accumulated) if (!(e = next_event())) return set_error(ctx, B200ZK_ERR_CUDA, "cudaEventCreate failed");
 
-    // ---- prep(g): task tables (counting sort of the <= task_len-entry tasks by length) + scatter, on seq ----------------
-    for (unsigned g = 0; g < ngroups; ++g) {
-        const Group& G = groups[g];
-        uint32_t* ntasks = ntasks_all + G.b0 + g;               // nbk + 1 entries per group
-        uint32_t* task_off = task_off_all + G.b0 + g;
-        uint32_t* task_bucket = task_bucket_all + G.task_base;
-        uint32_t* task_rank = task_rank_all + G.task_base;
-        uint32_t* order = order_all + G.task_base;
-        uint32_t* hist = hist_all + (size_t)g * (MAX_TASK_LEN + 1);
-        {
-            LaunchScope ls(ctx, st, "msm_tasks");
-            k_msm_task_counts<<<(G.nbk + 1 + 255) / 256, 256, 0, st>>>(offsets + G.b0, G.nbk, task_len, ntasks);
-        }
-        B2_TRY(check_launch(ctx, "k_msm_task_counts"));
-        B2_TRY(exclusive_scan(ctx, st, ntasks, task_off, sums, G.nbk + 1));
-        {
-            LaunchScope ls(ctx, st, "msm_tasks");
-            k_msm_fill_tasks<<<(G.nbk + 255) / 256, 256, 0, st>>>(task_off, G.nbk, task_bucket, multi_all + G.list_base, G.list_cap,
-                                                                  multi_all + 2 * g);
-        }
-        B2_TRY(check_launch(ctx, "k_msm_fill_tasks"));
-        {
-            LaunchScope ls(ctx, st, "msm_tasks");
-            k_msm_task_hist<<<(unsigned)((G.task_cap + 255) / 256), 256, 0, st>>>(offsets + G.b0, task_off, task_bucket, G.nbk, task_len, hist, task_rank);
-        }
-        {
-            LaunchScope ls(ctx, st, "msm_tasks");
-            k_msm_task_hist_scan<<<1, 1, 0, st>>>(hist, task_len);
-        }
-        {
-            LaunchScope ls(ctx, st, "msm_tasks");
-            k_msm_task_order<<<(unsigned)((G.task_cap + 255) / 256), 256, 0, st>>>(offsets + G.b0, task_off, task_bucket, G.nbk, task_len, hist, task_rank, order);
-        }
-        B2_TRY(check_launch(ctx, "k_msm_task_order"));
-        {
-            const size_t t0 = fold ? 0 : (size_t)G.set0 * n, cnt = fold ? total : (size_t)G.nsets * n;
-            LaunchScope ls(ctx, st, "msm_scatter");
-            k_msm_scatter<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(keys, ranks, offsets, (uint32_t)n, t0, cnt, fold ? 1u : 0u, entries);
-        }
-        B2_TRY(check_launch(ctx, "k_msm_scatter"));
-        B2_CUDA_OK(ctx, cudaEventRecord(G.prepped, st));
-    }
-
-    // ---- accumulate(g) on acc ---------------------------------------------------------------------------------------------
-    // the digit / sort phases above only read the scalars: a caller staging host buffers lets the H2D copy of
-    // the (2-4x larger) base array overlap them and signals its arrival here
     bool l2_window = false;
-    if (ctx->l2_persist_max && ctx->l2_window_max) {
+    if (nparts == 1 && ctx->l2_persist_max && ctx->l2_window_max) {
         // every base point is gathered once per window (W times per launch): pin the array in L2
         size_t bytes = n * sizeof(affine_t<F>);
         cudaStreamAttrValue attr;
         memset(&attr, 0, sizeof(attr));
-        attr.accessPolicyWindow.base_ptr = const_cast<void*>(d_bases);
+        attr.accessPolicyWindow.base_ptr = const_cast<void*>(parts[0].bases);
         attr.accessPolicyWindow.num_bytes = bytes < ctx->l2_window_max ? bytes : ctx->l2_window_max;
         double ratio = (double)ctx->l2_persist_max / (double)attr.accessPolicyWindow.num_bytes;
         attr.accessPolicyWindow.hitRatio = ratio > 1.0 ? 1.0f : (float)ratio;
@@ -766,18 +732,118 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
         l2_window = cudaStreamSetAttribute(ast, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess;
         cudaGetLastError();
     }
-    for (unsigned g = 0; g < ngroups; ++g) {
-        const Group& G = groups[g];
-        B2_CUDA_OK(ctx, cudaStreamWaitEvent(ast, G.prepped, 0));
-        {
-            LaunchScope ls(ctx, ast, acc_name);
-            k_msm_accumulate<F><<<(unsigned)((G.task_cap + 127) / 128), 128, 0, ast>>>(
-                reinterpret_cast<const affine_t<F>*>(d_bases), entries, offsets + G.b0, task_off_all + G.b0 + g, task_bucket_all + G.task_base,
-                order_all + G.task_base, G.nbk, task_len, (uint32_t)ctx->sm_count * (sizeof(F) > 32 ? B2_ACC_MINBLOCKS_G2 : B2_ACC_MINBLOCKS),
-                buckets + G.b0, task_sums_all + G.task_base);
+
+    for (unsigned p = 0; p < nparts; ++p) {
+        const MsmPart& P = parts[p];
+        const size_t np = P.n, total = (size_t)W * np;
+        uint32_t* keys = reinterpret_cast<uint32_t*>(ws + pw[p].keys);
+        uint32_t* ranks = reinterpret_cast<uint32_t*>(ws + pw[p].ranks);
+        uint32_t* entries = reinterpret_cast<uint32_t*>(ws + pw[p].entries);
+        uint32_t* counts = reinterpret_cast<uint32_t*>(ws + pw[p].counts);
+        uint32_t* offsets = reinterpret_cast<uint32_t*>(ws + pw[p].offsets);
+        uint32_t* ntasks_all = reinterpret_cast<uint32_t*>(ws + pw[p].ntasks);
+        uint32_t* task_off_all = reinterpret_cast<uint32_t*>(ws + pw[p].taskoff);
+        uint32_t* task_bucket_all = reinterpret_cast<uint32_t*>(ws + pw[p].taskbucket);
+        uint32_t* multi_all = reinterpret_cast<uint32_t*>(ws + pw[p].multi);
+        uint32_t* hist_all = reinterpret_cast<uint32_t*>(ws + pw[p].hist);
+        uint32_t* task_rank_all = reinterpret_cast<uint32_t*>(ws + pw[p].rank);
+        uint32_t* order_all = reinterpret_cast<uint32_t*>(ws + pw[p].order);
+        xyzz_t<F>* task_sums_all = reinterpret_cast<xyzz_t<F>*>(ws + pw[p].tasksums);
+        if (np == 0) {                                           // nothing to add: keep the event chain intact
+            for (unsigned g = 0; g < ngroups; ++g) {
+                B2_CUDA_OK(ctx, cudaEventRecord(prepped[(size_t)p * ngroups + g], st));
+                B2_CUDA_OK(ctx, cudaEventRecord(accumulated[(size_t)p * ngroups + g], ast));
+            }
+            continue;
         }
-        B2_TRY(check_launch(ctx, "k_msm_accumulate"));
-        B2_CUDA_OK(ctx, cudaEventRecord(G.accumulated, ast));
+        // ---- digits + scan of part p on seq (its scalars may still be arriving) ----------------------------------------------
+        if (P.scalars_ready) B2_CUDA_OK(ctx, cudaStreamWaitEvent(st, P.scalars_ready, 0));
+        B2_CUDA_OK(ctx, cudaMemsetAsync(counts, 0, ((size_t)nb + 1) * 4, st));
+        {
+            LaunchScope ls(ctx, st, "msm_digits");
+            if (glv) k_msm_digits_glv<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(reinterpret_cast<const Fr*>(P.scalars), (uint32_t)np, c,
+                                                                                   Wh, keys, ranks, counts);
+            else k_msm_digits<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(reinterpret_cast<const Fr*>(P.scalars), (uint32_t)np, c, W,
+                                                                              fold ? 1u : 0u, keys, ranks, counts);
+        }
+        B2_TRY(check_launch(ctx, "k_msm_digits"));
+        B2_TRY(exclusive_scan(ctx, st, counts, offsets, sums, nb + 1));
+        B2_CUDA_OK(ctx, cudaMemsetAsync(multi_all, 0, (size_t)ngroups * 8, st));          // [2 g], [2 g + 1] = big / small counts
+        B2_CUDA_OK(ctx, cudaMemsetAsync(hist_all, 0, (size_t)ngroups * (MAX_TASK_LEN + 1) * 4, st));
+
+        // ---- prep(g): task tables (counting sort of the <= task_len-entry tasks by length) + scatter, on seq ----------------
+        for (unsigned g = 0; g < ngroups; ++g) {
+            const Group& G = groups[g];
+            uint32_t* ntasks = ntasks_all + G.b0 + g;               // nbk + 1 entries per group
+            uint32_t* task_off = task_off_all + G.b0 + g;
+            uint32_t* task_bucket = task_bucket_all + G.task_base;
+            uint32_t* task_rank = task_rank_all + G.task_base;
+            uint32_t* order = order_all + G.task_base;
+            uint32_t* hist = hist_all + (size_t)g * (MAX_TASK_LEN + 1);
+            {
+                LaunchScope ls(ctx, st, "msm_tasks");
+                k_msm_task_counts<<<(G.nbk + 1 + 255) / 256, 256, 0, st>>>(offsets + G.b0, G.nbk, task_len, ntasks);
+            }
+            B2_TRY(check_launch(ctx, "k_msm_task_counts"));
+            B2_TRY(exclusive_scan(ctx, st, ntasks, task_off, sums, G.nbk + 1));
+            {
+                LaunchScope ls(ctx, st, "msm_tasks");
+                k_msm_fill_tasks<<<(G.nbk + 255) / 256, 256, 0, st>>>(task_off, G.nbk, task_bucket, multi_all + G.list_base, G.list_cap,
+                                                                      multi_all + 2 * g);
+            }
+            B2_TRY(check_launch(ctx, "k_msm_fill_tasks"));
+            {
+                LaunchScope ls(ctx, st, "msm_tasks");
+                k_msm_task_hist<<<(unsigned)((G.task_cap + 255) / 256), 256, 0, st>>>(offsets + G.b0, task_off, task_bucket, G.nbk, task_len, hist, task_rank);
+            }
+            {
+                LaunchScope ls(ctx, st, "msm_tasks");
+                k_msm_task_hist_scan<<<1, 1, 0, st>>>(hist, task_len);
+            }
+            {
+                LaunchScope ls(ctx, st, "msm_tasks");
+                k_msm_task_order<<<(unsigned)((G.task_cap + 255) / 256), 256, 0, st>>>(offsets + G.b0, task_off, task_bucket, G.nbk, task_len, hist, task_rank, order);
+            }
+            B2_TRY(check_launch(ctx, "k_msm_task_order"));
+            {
+                const size_t t0 = fold ? 0 : (size_t)G.set0 * np, cnt = fold ? total : (size_t)G.nsets * np;
+                LaunchScope ls(ctx, st, "msm_scatter");
+                k_msm_scatter<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(keys, ranks, offsets, (uint32_t)np, t0, cnt, fold ? 1u : 0u, entries);
+            }
+            B2_TRY(check_launch(ctx, "k_msm_scatter"));
+            B2_CUDA_OK(ctx, cudaEventRecord(prepped[(size_t)p * ngroups + g], st));
+        }
+
+        // ---- accumulate(g) of part p on acc: the sort phases above only read the scalars, the (2-4x larger) base array of a
+        //      host-staged part may still be on its way and signals its arrival here ------------------------------------------------
+        if (P.bases_ready) B2_CUDA_OK(ctx, cudaStreamWaitEvent(ast, P.bases_ready, 0));
+        for (unsigned g = 0; g < ngroups; ++g) {
+            const Group& G = groups[g];
+            B2_CUDA_OK(ctx, cudaStreamWaitEvent(ast, prepped[(size_t)p * ngroups + g], 0));
+            {
+                LaunchScope ls(ctx, ast, acc_name);
+                k_msm_accumulate<F><<<(unsigned)((G.task_cap + 127) / 128), 128, 0, ast>>>(
+                    reinterpret_cast<const affine_t<F>*>(P.bases), entries, offsets + G.b0, task_off_all + G.b0 + g, task_bucket_all + G.task_base,
+                    order_all + G.task_base, G.nbk, task_len, (uint32_t)ctx->sm_count * (sizeof(F) > 32 ? B2_ACC_MINBLOCKS_G2 : B2_ACC_MINBLOCKS),
+                    rmw, buckets + G.b0, task_sums_all + G.task_base);
+            }
+            B2_TRY(check_launch(ctx, "k_msm_accumulate"));
+            if (rmw) {
+                // several parts: the next part's bucket kernel reads what this part's merges write, so they stay on `acc`
+                {
+                    LaunchScope ls(ctx, ast, "msm_merge");
+                    k_msm_merge_tasks<F><<<2 * ctx->sm_count, 128, 0, ast>>>(multi_all + G.list_base, multi_all + 2 * g, task_off_all + G.b0 + g,
+                                                                            task_sums_all + G.task_base, rmw, buckets + G.b0);
+                }
+                {
+                    LaunchScope ls(ctx, ast, "msm_merge");
+                    k_msm_merge_small<F><<<4 * ctx->sm_count, 128, 0, ast>>>(multi_all + G.list_base, G.list_cap, multi_all + 2 * g + 1,
+                                                                            task_off_all + G.b0 + g, task_sums_all + G.task_base, rmw, buckets + G.b0);
+                }
+                B2_TRY(check_launch(ctx, "k_msm_merge_tasks"));
+            }
+            B2_CUDA_OK(ctx, cudaEventRecord(accumulated[(size_t)p * ngroups + g], ast));
+        }
     }
     if (l2_window) {
         cudaStreamAttrValue attr;
@@ -790,19 +856,22 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
     // ---- tail(g) on seq: merge, bucket reduction, window sums, Horner step ----------------------------------------------
     for (unsigned g = 0; g < ngroups; ++g) {
         const Group& G = groups[g];
-        B2_CUDA_OK(ctx, cudaStreamWaitEvent(st, G.accumulated, 0));
-        uint32_t* task_off = task_off_all + G.b0 + g;
-        {
-            LaunchScope ls(ctx, st, "msm_merge");
-            k_msm_merge_tasks<F><<<2 * ctx->sm_count, 128, 0, st>>>(multi_all + G.list_base, multi_all + 2 * g, task_off,
-                                                                   task_sums_all + G.task_base, buckets + G.b0);
+        for (unsigned p = 0; p < nparts; ++p) B2_CUDA_OK(ctx, cudaStreamWaitEvent(st, accumulated[(size_t)p * ngroups + g], 0));
+        if (!rmw) {
+            uint32_t* multi_all = reinterpret_cast<uint32_t*>(ws + pw[0].multi);
+            uint32_t* task_off = reinterpret_cast<uint32_t*>(ws + pw[0].taskoff) + G.b0 + g;
+            xyzz_t<F>* task_sums = reinterpret_cast<xyzz_t<F>*>(ws + pw[0].tasksums) + G.task_base;
+            {
+                LaunchScope ls(ctx, st, "msm_merge");
+                k_msm_merge_tasks<F><<<2 * ctx->sm_count, 128, 0, st>>>(multi_all + G.list_base, multi_all + 2 * g, task_off, task_sums, 0u, buckets + G.b0);
+            }
+            {
+                LaunchScope ls(ctx, st, "msm_merge");
+                k_msm_merge_small<F><<<4 * ctx->sm_count, 128, 0, st>>>(multi_all + G.list_base, G.list_cap, multi_all + 2 * g + 1, task_off, task_sums,
+                                                                       0u, buckets + G.b0);
+            }
+            B2_TRY(check_launch(ctx, "k_msm_merge_tasks"));
         }
-        {
-            LaunchScope ls(ctx, st, "msm_merge");
-            k_msm_merge_small<F><<<4 * ctx->sm_count, 128, 0, st>>>(multi_all + G.list_base, G.list_cap, multi_all + 2 * g + 1, task_off,
-                                                                   task_sums_all + G.task_base, buckets + G.b0);
-        }
-        B2_TRY(check_launch(ctx, "k_msm_merge_tasks"));
         {
             LaunchScope ls(ctx, st, "msm_reduce");
             k_msm_reduce_segments<F><<<(G.nsets * nseg + 127) / 128, 128, 0, st>>>(buckets + G.b0, G.nsets, B, seg_len,
@@ -827,6 +896,15 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
         B2_TRY(check_launch(ctx, "k_msm_horner"));
     }
     return finish();
+}
+
+// single-part convenience wrapper
+template <class F>
+static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, const void* d_bases, const void* d_scalars, size_t n,
+                        void* d_out, const char* acc_name, cudaEvent_t bases_ready, cudaEvent_t scalars_ready = nullptr,
+                        unsigned tab_c = 0, unsigned c_force = 0) {
+    const MsmPart part{d_bases, d_scalars, n, bases_ready, scalars_ready};
+    return msm_dev_impl<F>(ctx, ms, ws_buf, &part, 1, d_out, acc_name, tab_c, c_force);
 }
 
 static MsmStreams slot_streams(b200zk_ctx* ctx, Slot& sl, int aux) {
@@ -917,24 +995,22 @@ int msm_lane_dev(b200zk_ctx* ctx, const MsmLane& lane, int g2, unsigned tab_c, c
               : msm_dev_impl<Fq>(ctx, st, *lane.ws, d_bases, d_scalars, n, d_out, "msm_accumulate_g1", nullptr, nullptr, tab_c);
 }
 
-// Host-staged G1 MSM in two halves on two streams: the H2D copy of the second half and the latency-bound tail of the
-// first half overlap the bucket accumulation of the other half (the PCIe transfer is ~1/3 of the end-to-end time).
-// d_bases / d_scalars are the device staging buffers the caller is filling on `copy_stream`; ev[0..3] are recorded by the
-// caller after scalars-1, bases-1, scalars-2, bases-2 have been queued.  d_out2: two XYZZ partials.
-int msm_g1_two_halves_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_scalars, size_t n1, size_t n2,
-                          cudaEvent_t ev[4], void* d_out2) {
-    const char* b = reinterpret_cast<const char*>(d_bases);
-    const char* s = reinterpret_cast<const char*>(d_scalars);
-    char* out = reinterpret_cast<char*>(d_out2);
-    // both halves use the window of the whole length: with GLV, 2^19 points at c = 15 cost 18 bucket additions per scalar
-    // against 16 at c = 16, and the larger bucket reduction overlaps the other half anyway (e2e 5.44 -> 5.08 ms at 2^20)
-    const unsigned c = choose_window(n1 + n2);
-    B2_TRY(msm_dev_impl<Fq>(ctx, slot_streams(ctx, sl, 0), sl.ws_msm, b, s, n1, out, "msm_accumulate_g1", ev[1], ev[0], 0, c));
-    B2_TRY(msm_dev_impl<Fq>(ctx, slot_streams(ctx, sl, 1), sl.ws_msm_aux, b + n1 * 64, s + n1 * 32, n2, out + 128, "msm_accumulate_g1", ev[3], ev[2],
-                            0, c));
-    B2_CUDA_OK(ctx, cudaEventRecord(sl.aux_done, sl.aux_stream));
-    B2_CUDA_OK(ctx, cudaStreamWaitEvent(sl.stream, sl.aux_done, 0));
-    return B200ZK_OK;
+// Host-staged MSM in `nparts` pieces (api.cu): d_bases / d_scalars are the device staging buffers the caller is filling on its copy
+// stream; cnt[p] pairs per piece, ev_scalars[p] / ev_bases[p] recorded after the piece's scalars / bases have been queued.  One bucket
+// set, one reduction tail: see msm_dev_impl.
+int msm_parts_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_bases, const void* d_scalars, const size_t* cnt, unsigned nparts,
+                  const cudaEvent_t* ev_scalars, const cudaEvent_t* ev_bases, void* d_out) {
+    if (nparts == 0 || nparts > 16) return set_error(ctx, B200ZK_ERR_ARG, "1..16 input parts");
+    MsmPart parts[16];
+    const size_t PB = g2 ? 128 : 64;
+    size_t lo = 0;
+    for (unsigned p = 0; p < nparts; ++p) {
+        parts[p] = MsmPart{reinterpret_cast<const char*>(d_bases) + lo * PB, reinterpret_cast<const char*>(d_scalars) + lo * 32, cnt[p],
+                           ev_bases ? ev_bases[p] : nullptr, ev_scalars ? ev_scalars[p] : nullptr};
+        lo += cnt[p];
+    }
+    return g2 ? msm_dev_impl<Fq2>(ctx, slot_streams(ctx, sl, 0), sl.ws_msm, parts, nparts, d_out, "msm_accumulate_g2")
+              : msm_dev_impl<Fq>(ctx, slot_streams(ctx, sl, 0), sl.ws_msm, parts, nparts, d_out, "msm_accumulate_g1");
 }
 
 // out = sum of `count` XYZZ points at pts[i * stride] (no normalisation): combines gathered per-rank partials

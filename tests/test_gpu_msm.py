@@ -230,3 +230,34 @@ def test_2_26_linearity_generic_and_window_groups(net, cref):
     a, b, c = d_msm(bases, s, None, net), d_msm(bases, t, None, net), d_msm(bases, st, None, net)
     exp_sum, _ = cref.msm_g1(np.stack([a.limbs, b.limbs]), layout.fr_to_arr([1, 1]))
     assert not c.infinity and (c.limbs == exp_sum).all()
+
+
+def test_host_staged_parts_share_one_bucket_set(net, cref):
+    """b200zk_msm_g1 on host buffers >= 2^18 pairs travels in 4 parts whose bucket kernels add into ONE bucket set
+    (csrc/msm.cu, read-modify-write of the XYZZ buckets): random scalars, then a 0/1-heavy witness-like vector (giant
+    buckets: the multi-task merges of every part add into the shared buckets), equal points and opposite points that only
+    meet ACROSS parts (P + P and P + (-P) through the read-modify-write path), an infinity base and zero scalars."""
+    from oracle import layout, bn254 as o
+    n = (1 << 18) + 3
+    bases = cref.g1_generate(0xB2000018, n)
+    scalars = cref.fr_generate(0xB2000018, n)
+    q = n // 4
+    bases[q + 11] = bases[11]                              # same point in parts 0 and 1 ...
+    scalars[q + 11] = scalars[11]                          # ... with the same scalar: doubling inside a shared bucket
+    neg = layout.g1_to_arr([o.G1.neg(layout.arr_to_g1(bases[12:13])[0])])[0]
+    bases[3 * q + 12] = neg                                # P in part 0, -P in part 3, same scalar: the bucket empties again
+    scalars[3 * q + 12] = scalars[12]
+    bases[2 * q + 5] = 0                                   # infinity base
+    scalars[7] = 0
+    got = d_msm(bases, scalars, None, net)
+    exp, inf = cref.msm_g1(bases, scalars)
+    assert got.infinity == inf and (got.limbs == exp).all()
+    rng = np.random.default_rng(11)
+    small = layout.fr_to_arr([int(v) for v in rng.choice([0, 1, 1, 1, 1, 2, 3, 65535], size=n)])
+    got = d_msm(bases, small, None, net)
+    exp, inf = cref.msm_g1(bases, small)
+    assert got.infinity == inf and (got.limbs == exp).all()
+    b2, s2 = cref.g2_generate(0xB2000019, n), cref.fr_generate(0xB2000019, n)
+    got = d_msm(b2, s2, None, net, g2=True)
+    exp, inf = cref.msm_g2(b2, s2)
+    assert got.infinity == inf and (got.limbs == exp).all()
