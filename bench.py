@@ -564,15 +564,11 @@ def main():
     h_bases.copy_(bases)
     h_scalars.copy_(scalars)
     hb_np, hs_np = h_bases.numpy().view(np.uint64), h_scalars.numpy().view(np.uint64)
-    d_b2 = torch.empty_like(bases)
-    d_s2 = torch.empty_like(scalars)
 
     def step_e2e():
         if world == 1:
             return net.msm(hb_np, hs_np)                       # the C-ABI host-buffer call (b200zk_msm_g1)
-        d_b2.copy_(h_bases, non_blocking=True)
-        d_s2.copy_(h_scalars, non_blocking=True)
-        net.msm_dev(d_b2, d_s2, part)
+        net.msm_staged(hb_np, hs_np, part)                      # H2D in parts behind the bucket kernels (b200zk_msm_staged_dev)
         xch.sum(part, out=res_dev)
         return host_result()                                   # D2H of the affine result: the step's output reaches the host
 
@@ -704,7 +700,7 @@ def main():
                 gathered_inputs = (np.concatenate([x.cpu().numpy().view(np.uint64) for x in gb]),
                                    np.concatenate([x.cpu().numpy().view(np.uint64) for x in gs]))
                 del gb, gs
-        del bases, scalars, d_b2, d_s2
+        del bases, scalars
         torch.cuda.empty_cache()
         if not args.no_multi:
             multi = measure_multi_gpu(net, dev, rank, world, not args.no_cpu_baseline)

@@ -42,6 +42,7 @@ SIGNATURES = {
                                      ctypes.POINTER(ctypes.c_int)]),
     "b200zk_msm_g2": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, ctypes.c_size_t, c_vp, ctypes.c_size_t, c_vp,
                                      ctypes.POINTER(ctypes.c_int)]),
+    "b200zk_msm_staged_dev": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_size_t, c_vp, ctypes.c_size_t, c_vp]),
     "b200zk_msm_g1_dev": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "b200zk_msm_g2_dev": (ctypes.c_int, [c_vp, ctypes.c_int, c_vp, c_vp, ctypes.c_size_t, c_vp]),
     "b200zk_msm_table_windows": (ctypes.c_uint, [ctypes.c_uint]),

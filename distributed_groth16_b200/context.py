@@ -256,6 +256,18 @@ class Net:
         self.check(fn(self._h, int(sid), c_vp(bases.data_ptr()), c_vp(scalars.data_ptr()), n, c_vp(out_xyzz.data_ptr())))
         return out_xyzz
 
+    def msm_staged(self, bases, scalars, out_xyzz=None, g2: bool = False, sid: int = 0):
+        """Host numpy buffers in (pinned for full PCIe speed), this GPU's XYZZ partial out as a CUDA tensor: the transfer runs in
+        parts behind the bucket kernels (b200zk_msm_staged_dev)."""
+        import torch
+        w = 16 if g2 else 8
+        b, s = _as_u64(bases, w), _as_u64(scalars, 4)
+        if out_xyzz is None:
+            out_xyzz = torch.empty(32 if g2 else 16, dtype=torch.int64, device=self._dev())
+        self.check(self._lib.b200zk_msm_staged_dev(self._h, int(sid), 1 if g2 else 0, _ptr(b), b.shape[0] if b.size else 0, _ptr(s),
+                                                   s.shape[0] if s.size else 0, c_vp(out_xyzz.data_ptr())))
+        return out_xyzz
+
     def msm_table_windows(self, c: int) -> int:
         return int(self._lib.b200zk_msm_table_windows(int(c)))
 

@@ -196,6 +196,46 @@ uint64_t b200zk_launch_count(const b200zk_ctx* ctx) { return ctx ? ctx->launches
 }  // extern "C"
 
 // ---- MSM ---------------------------------------------------------------------------------------
+// Host buffers -> this device's XYZZ partial in d_out (device memory), stream-ordered on the slot's stream.  Large inputs travel
+// in parts on the copy stream (scalars of part p, bases of part p, scalars of part p + 1, ...): the sort phases of a part start when
+// its scalars are there, its bucket kernel when its bases are, and every part adds into the same bucket set -- the PCIe transfer of
+// part p + 1 hides behind the bucket kernel of part p (msm.cu, msm_dev_impl).  The host buffers may be reused once the copy stream
+// has drained, which `wait_copies` does before returning.  Caller holds the slot mutex and has made the device current.
+namespace b200zk {
+int msm_staged_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* bases, const void* scalars, size_t n, void* d_out, bool wait_copies) {
+    const size_t PB = g2 ? 128 : 64;
+    B2_CUDA_OK(ctx, sl.io_a.reserve(n * PB + n * 32 + 64));
+    char* d_bases = reinterpret_cast<char*>(sl.io_a.p);
+    char* d_scalars = d_bases + n * PB;
+    static const int parts_env = getenv("B200ZK_MSM_PARTS") ? atoi(getenv("B200ZK_MSM_PARTS")) : 0;
+    unsigned nparts = parts_env > 0 ? (unsigned)parts_env : (n >= ((size_t)1 << 18) ? 4u : 1u);
+    if (nparts > 16) nparts = 16;
+    const char* hb = reinterpret_cast<const char*>(bases);
+    const char* hs = reinterpret_cast<const char*>(scalars);
+    cudaStream_t cs = sl.copy_stream;
+    size_t cnt[16];
+    cudaEvent_t ev_s[16], ev_b[16];
+    size_t lo = 0;
+    for (unsigned p = 0; p < nparts; ++p) {
+        const size_t hi = (size_t)(((unsigned __int128)n * (p + 1)) / nparts);
+        cnt[p] = hi - lo;
+        ev_s[p] = ev_b[p] = nullptr;
+        if (cnt[p]) {
+            B2_CUDA_OK(ctx, cudaMemcpyAsync(d_scalars + lo * 32, hs + lo * 32, cnt[p] * 32, cudaMemcpyHostToDevice, cs));
+            B2_CUDA_OK(ctx, cudaEventRecord(sl.stage_ev[2 * p], cs));
+            B2_CUDA_OK(ctx, cudaMemcpyAsync(d_bases + lo * PB, hb + lo * PB, cnt[p] * PB, cudaMemcpyHostToDevice, cs));
+            B2_CUDA_OK(ctx, cudaEventRecord(sl.stage_ev[2 * p + 1], cs));
+            ev_s[p] = sl.stage_ev[2 * p];
+            ev_b[p] = sl.stage_ev[2 * p + 1];
+        }
+        lo = hi;
+    }
+    B2_TRY(msm_parts_dev(ctx, sl, g2, d_bases, d_scalars, cnt, nparts, ev_s, ev_b, d_out));
+    if (wait_copies) B2_CUDA_OK(ctx, cudaStreamSynchronize(cs));
+    return B200ZK_OK;
+}
+}  // namespace b200zk
+
 template <int G2>
 static int msm_host(b200zk_ctx* ctx, int stream, const uint64_t* bases, size_t n_bases, const uint64_t* scalars,
                     size_t n_scalars, uint64_t* out_affine, int* out_is_inf) {
@@ -210,58 +250,14 @@ static int msm_host(b200zk_ctx* ctx, int stream, const uint64_t* bases, size_t n
     Slot& sl = ctx->slots[stream];
     std::lock_guard<std::mutex> g(sl.mu);
     B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));
-    B2_CUDA_OK(ctx, sl.io_a.reserve(n * PB + n * 32 + 64));
     B2_CUDA_OK(ctx, sl.small.reserve(1024));
-    char* d_bases = reinterpret_cast<char*>(sl.io_a.p);
-    char* d_scalars = d_bases + n * PB;
-    // Large inputs travel in parts on the copy stream (scalars of part p, bases of part p, scalars of part p + 1, ...): the sort
-    // phases of a part start when its scalars are there, its bucket kernel when its bases are, and every part adds into the
-    // same bucket set -- the PCIe transfer of part p + 1 hides behind the bucket kernel of part p (msm.cu, msm_dev_impl).
-    static const int parts_env = getenv("B200ZK_MSM_PARTS") ? atoi(getenv("B200ZK_MSM_PARTS")) : 0;
-    unsigned nparts = parts_env > 0 ? (unsigned)parts_env : (n >= ((size_t)1 << 18) ? 4u : 1u);
-    if (nparts > 16) nparts = 16;
-    if (nparts > 1) {
-        const char* hb = reinterpret_cast<const char*>(bases);
-        const char* hs = reinterpret_cast<const char*>(scalars);
-        cudaStream_t cs = sl.copy_stream;
-        size_t cnt[16];
-        cudaEvent_t ev_s[16], ev_b[16];
-        size_t lo = 0;
-        for (unsigned p = 0; p < nparts; ++p) {
-            const size_t hi = (size_t)(((unsigned __int128)n * (p + 1)) / nparts);
-            cnt[p] = hi - lo;
-            B2_CUDA_OK(ctx, cudaMemcpyAsync(d_scalars + lo * 32, hs + lo * 32, cnt[p] * 32, cudaMemcpyHostToDevice, cs));
-            B2_CUDA_OK(ctx, cudaEventRecord(sl.stage_ev[2 * p], cs));
-            B2_CUDA_OK(ctx, cudaMemcpyAsync(d_bases + lo * PB, hb + lo * PB, cnt[p] * PB, cudaMemcpyHostToDevice, cs));
-            B2_CUDA_OK(ctx, cudaEventRecord(sl.stage_ev[2 * p + 1], cs));
-            ev_s[p] = sl.stage_ev[2 * p];
-            ev_b[p] = sl.stage_ev[2 * p + 1];
-            lo = hi;
-        }
-        char* sm = reinterpret_cast<char*>(sl.small.p);
-        B2_TRY(msm_parts_dev(ctx, sl, G2, d_bases, d_scalars, cnt, nparts, ev_s, ev_b, sm));
-        B2_TRY(G2 ? g2_sum_dev(ctx, sl, sm, 1, sm + XB) : g1_sum_dev(ctx, sl, sm, 1, sm + XB));
-        uint64_t hostp[17];
-        B2_CUDA_OK(ctx, cudaMemcpyAsync(hostp, sm + XB, PB + 8, cudaMemcpyDeviceToHost, sl.stream));
-        B2_CUDA_OK(ctx, cudaStreamSynchronize(sl.stream));
-        B2_CUDA_OK(ctx, cudaStreamSynchronize(cs));
-        memcpy(out_affine, hostp, PB);
-        *out_is_inf = (int)hostp[PB / 8];
-        return B200ZK_OK;
-    }
-    if (n) {
-        // scalars first on the compute stream; the bases travel on the copy stream while digits/sort run
-        B2_CUDA_OK(ctx, cudaMemcpyAsync(d_scalars, scalars, n * 32, cudaMemcpyHostToDevice, sl.stream));
-        B2_CUDA_OK(ctx, cudaMemcpyAsync(d_bases, bases, n * PB, cudaMemcpyHostToDevice, sl.copy_stream));
-        B2_CUDA_OK(ctx, cudaEventRecord(sl.copy_done, sl.copy_stream));
-    }
     char* sm = reinterpret_cast<char*>(sl.small.p);
-    cudaEvent_t ready = n ? sl.copy_done : nullptr;
-    B2_TRY(G2 ? msm_g2_dev(ctx, sl, d_bases, d_scalars, n, sm, ready) : msm_g1_dev(ctx, sl, d_bases, d_scalars, n, sm, ready));
+    B2_TRY(msm_staged_dev(ctx, sl, G2, bases, scalars, n, sm, false));
     B2_TRY(G2 ? g2_sum_dev(ctx, sl, sm, 1, sm + XB) : g1_sum_dev(ctx, sl, sm, 1, sm + XB));
     uint64_t host[17];
     B2_CUDA_OK(ctx, cudaMemcpyAsync(host, sm + XB, PB + 8, cudaMemcpyDeviceToHost, sl.stream));
     B2_CUDA_OK(ctx, cudaStreamSynchronize(sl.stream));
+    B2_CUDA_OK(ctx, cudaStreamSynchronize(sl.copy_stream));
     memcpy(out_affine, host, PB);
     *out_is_inf = (int)host[PB / 8];
     return B200ZK_OK;
@@ -294,6 +290,17 @@ int b200zk_msm_g1(b200zk_ctx* ctx, int stream, const uint64_t* bases, size_t n_b
 int b200zk_msm_g2(b200zk_ctx* ctx, int stream, const uint64_t* bases, size_t n_bases, const uint64_t* scalars,
                   size_t n_scalars, uint64_t out_affine[16], int* out_is_inf) {
     return msm_host<1>(ctx, stream, bases, n_bases, scalars, n_scalars, out_affine, out_is_inf);
+}
+
+int b200zk_msm_staged_dev(b200zk_ctx* ctx, int stream, int g2, const uint64_t* bases, size_t n_bases, const uint64_t* scalars,
+                          size_t n_scalars, void* d_out_xyzz) {
+    if (!ctx || !valid_slot(stream) || !d_out_xyzz) return B200ZK_ERR_ARG;
+    if (n_bases != n_scalars) return set_error(ctx, B200ZK_ERR_LENGTH, std::to_string(n_bases < n_scalars ? n_bases : n_scalars));
+    if (n_bases && (!bases || !scalars)) return B200ZK_ERR_ARG;
+    Slot& sl = ctx->slots[stream];
+    std::lock_guard<std::mutex> g(sl.mu);
+    B2_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+    return msm_staged_dev(ctx, sl, g2, bases, scalars, n_bases, d_out_xyzz, true);
 }
 
 int b200zk_msm_g1_dev(b200zk_ctx* ctx, int stream, const void* d_bases, const void* d_scalars, size_t n, void* d_out) {

@@ -203,6 +203,8 @@ int msm_g2_dev(b200zk_ctx* ctx, Slot& sl, const void* d_bases, const void* d_sca
                cudaEvent_t bases_ready = nullptr, int aux = 0);
 int msm_parts_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_bases, const void* d_scalars, const size_t* cnt, unsigned nparts,
                   const cudaEvent_t* ev_scalars, const cudaEvent_t* ev_bases, void* d_out_xyzz);
+// api.cu: host buffers -> device partial, staged in parts
+int msm_staged_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* bases, const void* scalars, size_t n, void* d_out, bool wait_copies);
 unsigned msm_table_windows(unsigned c);
 unsigned msm_table_auto_window(size_t n);
 int msm_table_build_dev(b200zk_ctx* ctx, Slot& sl, int g2, const void* d_bases, size_t n, unsigned c, void* d_table);

@@ -228,18 +228,10 @@ int group_msm(b200zk_group* grp, const uint64_t* bases, size_t n_bases, const ui
         Slot& sl = ctx->slots[0];
         G_CUDA_OK(grp, cudaSetDevice(ctx->device));
         const size_t lo = cut(n, g, P), cnt = cut(n, g + 1, P) - lo;
-        G_CUDA_OK(grp, sl.io_a.reserve(cnt * (PB + 32) + 64));
         G_CUDA_OK(grp, sl.small.reserve(4096));
-        char* d_bases = reinterpret_cast<char*>(sl.io_a.p);
-        char* d_scalars = d_bases + cnt * PB;
-        cudaEvent_t ready = nullptr;
-        if (cnt) {
-            G_CUDA_OK(grp, cudaMemcpyAsync(d_scalars, reinterpret_cast<const char*>(scalars) + lo * 32, cnt * 32, cudaMemcpyHostToDevice, sl.stream));
-            G_CUDA_OK(grp, cudaMemcpyAsync(d_bases, reinterpret_cast<const char*>(bases) + lo * PB, cnt * PB, cudaMemcpyHostToDevice, sl.copy_stream));
-            G_CUDA_OK(grp, cudaEventRecord(sl.copy_done, sl.copy_stream));
-            ready = sl.copy_done;
-        }
-        G_TRY(grp, g, G2 ? msm_g2_dev(ctx, sl, d_bases, d_scalars, cnt, sl.small.p, ready) : msm_g1_dev(ctx, sl, d_bases, d_scalars, cnt, sl.small.p, ready));
+        // this device's index range, staged in parts behind its own bucket kernels (api.cu, msm_staged_dev)
+        G_TRY(grp, g, msm_staged_dev(ctx, sl, G2, reinterpret_cast<const char*>(bases) + lo * PB, reinterpret_cast<const char*>(scalars) + lo * 32,
+                                     cnt, sl.small.p, false));
         G_CUDA_OK(grp, cudaEventRecord(grp->ev_done[g], sl.stream));
     }
     // partials -> device 0 (peer copies), sum, normalise
@@ -257,6 +249,10 @@ int group_msm(b200zk_group* grp, const uint64_t* bases, size_t n_bases, const ui
     G_CUDA_OK(grp, cudaMemcpyAsync(host, sm + 3584, PB + 8, cudaMemcpyDeviceToHost, s0.stream));
     G_CUDA_OK(grp, cudaStreamSynchronize(s0.stream));
     int rc = sync_all(grp);
+    for (int g = 0; g < P && !rc; ++g) {                      // the host buffers are free again once every copy stream drained
+        cudaSetDevice(grp->ctx[g]->device);
+        if (cudaStreamSynchronize(grp->ctx[g]->slots[0].copy_stream) != cudaSuccess) rc = gerr(grp, B200ZK_ERR_CUDA, "copy stream failed");
+    }
     if (rc) return rc;
     memcpy(out_affine, host, PB);
     *out_is_inf = (int)host[PB / 8];

@@ -63,6 +63,12 @@ int b200zk_msm_g1(b200zk_ctx* ctx, int stream, const uint64_t* bases, size_t n_b
                   const uint64_t* scalars, size_t n_scalars, uint64_t out_affine[8], int* out_is_inf);
 int b200zk_msm_g2(b200zk_ctx* ctx, int stream, const uint64_t* bases, size_t n_bases,
                   const uint64_t* scalars, size_t n_scalars, uint64_t out_affine[16], int* out_is_inf);
+/* Host buffers in, this GPU's partial sum out (XYZZ, device memory, ordered on slot `stream`): the input travels over PCIe in
+ * parts whose bucket kernels add into one bucket set, so the transfer hides behind the compute.  The multi-GPU callers use it
+ * for their index range and combine the partials (b200zk_msm_exchange_sum_dev, b200zk_group_msm_*).  Returns once the host
+ * buffers may be reused. */
+int b200zk_msm_staged_dev(b200zk_ctx* ctx, int stream, int g2, const uint64_t* bases, size_t n_bases, const uint64_t* scalars,
+                          size_t n_scalars, void* d_out_xyzz);
 /* Device buffers (inputs already resident in HBM).  `d_out_xyzz` receives the un-normalised
  * partial sum (G1: 4 x 32 B = X,Y,ZZ,ZZZ; G2: 4 x 64 B) so that rank partials can be exchanged
  * and combined with b200zk_g{1,2}_sum_dev -- the multi-GPU replacement of the king's gather +
