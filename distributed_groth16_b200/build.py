@@ -38,7 +38,10 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str | Non
     global OBJ
     lib = out or LIB
     if not force and not defines and os.path.exists(lib) and os.path.getmtime(lib) >= _deps_mtime():
+        sys.stderr.write("distributed_groth16_b200.build: %s is newer than every source under csrc/ and include/: reused "
+                         "(build(force=True) recompiles)\n" % os.path.relpath(lib))
         return lib
+    sys.stderr.write("distributed_groth16_b200.build: compiling %d translation units for sm_100a with %s\n" % (len(SOURCES), _nvcc()))
     obj_dir = OBJ if not out else OBJ + "_" + os.path.basename(out).replace(".so", "")
     os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()

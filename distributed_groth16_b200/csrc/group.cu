@@ -52,6 +52,13 @@ struct b200zk_group_pk {
 
 namespace {
 
+// the group calls hop between devices; the caller's current device (which frameworks such as torch cache) is restored on exit
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 int gerr(b200zk_group* g, int code, const std::string& msg) {
     if (g) g->last_error = msg;
     return code;
@@ -215,6 +222,7 @@ size_t cut(size_t n, int g, int P) { return (size_t)(((unsigned __int128)n * (un
 template <int G2>
 int group_msm(b200zk_group* grp, const uint64_t* bases, size_t n_bases, const uint64_t* scalars, size_t n_scalars, uint64_t* out_affine,
               int* out_is_inf) {
+    DeviceGuard dev_guard;
     if (!grp || !out_affine || !out_is_inf) return B200ZK_ERR_ARG;
     if (n_bases != n_scalars) return gerr(grp, B200ZK_ERR_LENGTH, std::to_string(n_bases < n_scalars ? n_bases : n_scalars));
     const size_t n = n_bases;
@@ -286,6 +294,7 @@ int sharded_h(b200zk_group* grp, Fr* const* a, Fr* const* b, Fr* const* c, Fr* c
 extern "C" {
 
 int b200zk_group_create(const int* device_ids, int n_dev, b200zk_group** out) {
+    DeviceGuard dev_guard;
     if (!device_ids || !out || n_dev < 1 || n_dev > 8 || (n_dev & (n_dev - 1))) return B200ZK_ERR_ARG;
     b200zk_group* grp = new b200zk_group();
     grp->n = n_dev;
@@ -319,6 +328,7 @@ int b200zk_group_create(const int* device_ids, int n_dev, b200zk_group** out) {
 }
 
 void b200zk_group_destroy(b200zk_group* grp) {
+    DeviceGuard dev_guard;
     if (!grp) return;
     for (size_t g = 0; g < grp->ctx.size(); ++g) {
         cudaSetDevice(grp->ctx[g]->device);
@@ -345,6 +355,7 @@ int b200zk_group_msm_g2(b200zk_group* grp, const uint64_t* bases, size_t n_bases
 }
 
 int b200zk_group_ntt_fr(b200zk_group* grp, uint64_t* data, unsigned log_n, int inverse) {
+    DeviceGuard dev_guard;
     if (!grp || !data) return B200ZK_ERR_ARG;
     if (log_n > 28) return gerr(grp, B200ZK_ERR_DOMAIN, "log n > 28");
     const int P = grp->n;
@@ -374,6 +385,7 @@ int b200zk_group_ntt_fr(b200zk_group* grp, uint64_t* data, unsigned log_n, int i
 }
 
 int b200zk_group_h_circom(b200zk_group* grp, const uint64_t* a, const uint64_t* b, const uint64_t* c, unsigned log_m, uint64_t* h_out) {
+    DeviceGuard dev_guard;
     if (!grp || !a || !b || !c || !h_out) return B200ZK_ERR_ARG;
     if (log_m + 1 > 28) return gerr(grp, B200ZK_ERR_DOMAIN, "2m exceeds the 2^28 subgroup (PolynomialDegreeTooLarge)");
     const int P = grp->n;
@@ -404,6 +416,7 @@ int b200zk_group_h_circom(b200zk_group* grp, const uint64_t* a, const uint64_t* 
 
 // ---- sharded proving key + prove (BASELINE config 5) ------------------------------------------------------------------------
 void b200zk_group_pk_free(b200zk_group* grp, b200zk_group_pk* pk) {
+    DeviceGuard dev_guard;
     if (!pk) return;
     for (size_t g = 0; g < pk->shard.size(); ++g) {
         if (grp && g < grp->ctx.size()) cudaSetDevice(grp->ctx[g]->device);
@@ -419,6 +432,7 @@ void b200zk_group_pk_free(b200zk_group* grp, b200zk_group_pk* pk) {
 int b200zk_group_pk_upload(b200zk_group* grp, const uint64_t* a_query, const uint64_t* b_g1_query, const uint64_t* b_g2_query,
                            const uint64_t* l_query, const uint64_t* h_query, size_t n_vars, size_t n_inputs, size_t m,
                            const uint64_t* vk_points, b200zk_group_pk** out) {
+    DeviceGuard dev_guard;
     if (!grp || !out || !a_query || !b_g1_query || !b_g2_query || !h_query || !vk_points) return B200ZK_ERR_ARG;
     if (n_vars == 0 || n_inputs == 0 || n_inputs > n_vars) return gerr(grp, B200ZK_ERR_ARG, "need 1 <= n_inputs <= n_vars");
     if (m == 0 || (m & (m - 1))) return gerr(grp, B200ZK_ERR_DOMAIN, "h_query length must be a power of two");
@@ -511,6 +525,7 @@ size_t b200zk_group_pk_table_bytes(const b200zk_group_pk* pk) { return pk ? pk->
 
 int b200zk_group_groth16_prove(b200zk_group* grp, const b200zk_group_pk* pk, const uint64_t* z, const uint64_t* a, const uint64_t* b,
                                const uint64_t* c, const uint64_t r[4], const uint64_t s[4], uint8_t proof_out[128]) {
+    DeviceGuard dev_guard;
     if (!grp || !pk || !z || !a || !b || !c || !r || !s || !proof_out) return B200ZK_ERR_ARG;
     if (pk->n != grp->n) return gerr(grp, B200ZK_ERR_ARG, "proving key was sharded for a different group");
     const int P = grp->n;

@@ -112,10 +112,20 @@ def read_zkey(buf: bytes) -> ZKey:
             raise FormatError("zkey section %d too short" % sid)
         return _limbs(buf, o, count, width)
 
-    o4, _ = secs[4][0]
+    if n_vars == 0 or n_public + 1 > n_vars:
+        raise FormatError("zkey header: n_public + 1 = %d variables are public but n_vars = %d" % (n_public + 1, n_vars))
+    if domain_size == 0 or domain_size & (domain_size - 1):
+        raise FormatError("zkey header: domain size %d is not a power of two" % domain_size)
+    o4, l4 = secs[4][0]
     ncoef = struct.unpack_from("<I", buf, o4)[0]
+    if l4 < 4 + ncoef * 44:
+        raise FormatError("zkey coefficient section too short for %d records" % ncoef)
     rec = np.frombuffer(buf, dtype=np.dtype([("m", "<u4"), ("c", "<u4"), ("s", "<u4"), ("v", "<u8", (4,))]), count=ncoef,
                         offset=o4 + 4)
+    # the device kernels index z[col] and the QAP rows with these values unchecked (csrc/qap.cu): reject what the reference
+    # would panic on (index out of bounds) here, on the host
+    if ncoef and (int(rec["m"].max()) > 1 or int(rec["s"].max()) >= n_vars or int(rec["c"].max()) >= domain_size):
+        raise FormatError("zkey coefficient section: matrix index > 1, signal index >= n_vars or constraint index >= domain size")
     return ZKey(n_vars=n_vars, n_public=n_public, domain_size=domain_size, alpha_g1=alpha_g1, beta_g1=beta_g1,
                 beta_g2=beta_g2, gamma_g2=gamma_g2, delta_g1=delta_g1, delta_g2=delta_g2,
                 ic=sec(3, n_public + 1, 8), a_query=sec(5, n_vars, 8), b_g1_query=sec(6, n_vars, 8),
@@ -163,17 +173,24 @@ def read_r1cs(buf: bytes) -> R1CS:
     n_wires, n_pub_out, n_pub_in, n_prv_in = struct.unpack_from("<IIII", buf, off)
     off += 16 + 8
     n_constraints = struct.unpack_from("<I", buf, off)[0]
-    off, _ = secs[2][0]
+    off, l2 = secs[2][0]
+    end2 = off + l2
     rows = [[], [], []]
     cols = [[], [], []]
     vals = [[], [], []]
     term = np.dtype([("w", "<u4"), ("v", "<u8", (4,))])
     for i in range(n_constraints):
         for k in range(3):
+            if off + 4 > end2:
+                raise FormatError("r1cs constraint section ends inside constraint %d" % i)
             nterm = struct.unpack_from("<I", buf, off)[0]
             off += 4
+            if off + nterm * 36 > end2:
+                raise FormatError("r1cs constraint section ends inside constraint %d" % i)
             t = np.frombuffer(buf, dtype=term, count=nterm, offset=off)
             off += nterm * 36
+            if nterm and int(t["w"].max()) >= n_wires:
+                raise FormatError("r1cs constraint %d names wire %d of %d" % (i, int(t["w"].max()), n_wires))
             rows[k].append(np.full(nterm, i, dtype=np.uint32))
             cols[k].append(t["w"].astype(np.uint32))
             vals[k].append(t["v"].astype(np.uint64).reshape(nterm, 4))

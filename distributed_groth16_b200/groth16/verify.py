@@ -9,7 +9,7 @@ import ctypes
 
 import numpy as np
 
-from ..ark_serialize import ArkVerifyingKey, deserialize_proof
+from ..ark_serialize import ArkVerifyingKey, deserialize_proof, serialize_proof
 from ..context import Net, _as_u64, _ptr
 
 
@@ -20,7 +20,14 @@ def verify_proof(net: Net, vk: ArkVerifyingKey, public_inputs, proof) -> bool:
     if isinstance(proof, (bytes, bytearray, memoryview)):
         a, b, c = deserialize_proof(net, bytes(proof), check_subgroup=True)
     else:
+        # raw limb tuples get the validation the byte form gets for free: a round trip through the compressed encoding
+        # rebuilds y from x (on-curve) and runs the G2 subgroup check; anything that does not come back unchanged is rejected
         a, b, c = proof
+        a, c = _as_u64(a, 8).reshape(-1), _as_u64(c, 8).reshape(-1)
+        b = _as_u64(b, 16).reshape(-1)
+        a2, b2, c2 = deserialize_proof(net, serialize_proof(net, a, b, c), check_subgroup=True)
+        if not ((a2 == a).all() and (b2 == b).all() and (c2 == c).all()):
+            raise ValueError("proof points are not valid curve points")
     a, c = _as_u64(a, 8).reshape(-1), _as_u64(c, 8).reshape(-1)
     b = _as_u64(b, 16).reshape(-1)
     ic = _as_u64(vk.gamma_abc_g1, 8)

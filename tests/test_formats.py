@@ -47,3 +47,28 @@ def test_readers_on_the_reference_fixtures():
     ref = o.read_r1cs(open(REF + "/ark-circom/test-vectors/complex-circuit/complex-circuit-10000-10000.r1cs", "rb").read())
     mine = formats.read_r1cs(open(REF + "/ark-circom/test-vectors/complex-circuit/complex-circuit-10000-10000.r1cs", "rb").read())
     assert mine.n_constraints == ref["n_constraints"] and int(mine.cols[0][0]) == ref["constraints"][0][0][0][1]
+
+
+def test_readers_reject_out_of_range_indices():
+    """A malformed zkey / r1cs must fail on the host (FormatError), not index device memory out of bounds: the reference panics
+    on the same inputs (index out of bounds in ark-circom/src/zkey.rs / circom/r1cs_reader.rs)."""
+    import struct
+    import artefact_writer as aw
+    from distributed_groth16_b200 import formats
+    d = np.load(os.path.join(G, "complex_circuit.zkey.pk.npz"))
+    good = bytearray(aw.write_zkey(d))
+    zk = formats.read_zkey(bytes(good))
+    secs = formats._sections(bytes(good), b"zkey")
+    o4, _ = secs[4][0]
+    bad = bytearray(good)
+    struct.pack_into("<I", bad, o4 + 4 + 8, zk.n_vars + 5)             # signal index of the first coefficient record
+    with pytest.raises(formats.FormatError):
+        formats.read_zkey(bytes(bad))
+    bad = bytearray(good)
+    struct.pack_into("<I", bad, o4 + 4, 7)                             # matrix index > 1
+    with pytest.raises(formats.FormatError):
+        formats.read_zkey(bytes(bad))
+    bad = bytearray(good)
+    struct.pack_into("<I", bad, o4, 0x7FFFFFFF)                        # record count far beyond the section
+    with pytest.raises(formats.FormatError):
+        formats.read_zkey(bytes(bad))

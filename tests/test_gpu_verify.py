@@ -72,3 +72,14 @@ def test_degenerate_inputs(net):
     assert not verify.verify_proof(net, vk, layout.fr_to_arr(pub), (a, zero2, zero1))
     vk0 = ark.ArkVerifyingKey(vk.alpha_g1, vk.beta_g2, vk.gamma_g2, vk.delta_g2, vk.gamma_abc_g1[:1])
     assert not verify.verify_proof(net, vk0, [], (a, b, c))
+
+
+def test_raw_limb_proofs_are_validated_like_the_byte_form(net):
+    """(A, B, C) given as limb arrays: an off-curve point is rejected (the byte form rejects it at decompression)."""
+    from oracle import layout
+    vk, pub, (a, b, c) = _snarkjs_million()
+    assert verify.verify_proof(net, vk, layout.fr_to_arr(pub), (a, b, c))
+    bad = np.array(a, dtype=np.uint64, copy=True).reshape(-1)
+    bad[4] ^= np.uint64(1)                                   # y changed: no longer on y^2 = x^3 + 3
+    with pytest.raises(ValueError):
+        verify.verify_proof(net, vk, layout.fr_to_arr(pub), (bad, b, c))
