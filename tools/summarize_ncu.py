@@ -21,7 +21,9 @@ def launches(path, tag):
         a[1] += ns
     total = sum(v[1] for v in agg.values())
     out = ["# ncu launch list summary (%s)" % tag, "",
-           "command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 200 python bench.py --steps 2 --warmup 1`",
+           "command: `ncu --metrics gpu__time_duration.sum --clock-control none -c 400 python bench.py --steps 2 --warmup 1 "
+           "--no-prove --no-sizes --no-cpu-baseline` (input generation, 3 warm-up + 2 timed + 2 end-to-end steps, the pipelined and "
+           "fixed-base sections)",
            "(cold-cache, serialised launches: compare SHARES, not absolutes)", "",
            "| kernel | launches | total ms | share |", "|---|---|---|---|"]
     for k, (n, ns) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
