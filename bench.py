@@ -140,14 +140,24 @@ def measure_ntt(net, hbm_peak, pipe_peak):
     ms = sum(ts) / len(ts)
     back = torch.empty_like(x)
     net.ntt_dev(y, back, inverse=True)
+    # products per element, as csrc/ntt.cu runs it: passes of <= 8 butterfly levels whose first level has unit twiddles, and at
+    # every pass boundary the inter-pass twiddle: 2 products through the two-level power table, 1 where a single-level table
+    # exists (middle passes with <= 2^16 distinct exponents)
     passes = -(-log_n // 8)
-    products = n * (log_n / 2.0 + 2.0 * (passes - 1))
+    log_r = [log_n // passes + (1 if i < log_n % passes else 0) for i in range(passes)]
+    per_elem, log_l = (log_n - passes) / 2.0, 0
+    for i in range(passes - 1):
+        per_elem += 1.0 if (i > 0 and log_n - log_l <= 16) else 2.0
+        log_l += log_r[i]
+    products = n * per_elem
     return {"metric": "Fr NTT 2^%d (BN254 scalar field)" % log_n, "ms": ms, "ms_min": ts[0], "gelem_s": n / ms / 1e6,
             "roofline": {"bound": "hbm", "achieved": 64.0 * n / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
                          "frac": 64.0 * n / ms / 1e6 / hbm_peak, "algorithmic_bytes_per_element": 64,
                          "pipe": {"achieved": products / ms / 1e6, "peak": pipe_peak, "unit": "G modular products/s",
                                   "frac": products / ms / 1e6 / pipe_peak,
-                                  "how": "n x (log n / 2 butterflies + 2 twiddle products per element per pass boundary)"}},
+                                  "products_per_element": per_elem,
+                                  "how": "n x ((log n - passes) / 2 butterfly products + 2 (two-level table) or 1 (single-level) twiddle "
+                                         "products per pass boundary)"}},
             "round_trip_exact": bool((back == x).all()),
             "timing": "CUDA events per transform, L2 flushed between transforms, 10 runs after 3 warm-ups"}
 

@@ -655,6 +655,13 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
     while (task_len < MAX_TASK_LEN && (uint64_t)task_len * nb < 3 * (uint64_t)total_max &&
            total_max / (2 * task_len) + nb >= (1u << 19))
         task_len *= 2;
+    // Small inputs cannot fill the machine with 128-entry tasks, and a real witness (29 821 of the 29 823 entries of the
+    // reference's sha256 witness are 0 or 1, groth16/examples/sha256.rs:182-185) puts thousands of entries into ONE bucket:
+    // 118 serial chains of 128 additions = 0.6 ms for a 30 k-point MSM.  Shorter tasks turn that bucket into ~900 parallel
+    // chains of 16 plus a block-level tree (k_msm_merge_tasks); buckets that stay below 16 entries are unaffected.
+    static const bool short_env = !(getenv("B200ZK_MSM_SHORT_TASKS") && getenv("B200ZK_MSM_SHORT_TASKS")[0] == '0');
+    if (short_env && n_max <= (1u << 16))
+        while (task_len > 16 && total_max / task_len < (1u << 17)) task_len /= 2;
     const size_t max_tasks = total_max / task_len + nb + ngroups;             // per part, all groups together
     size_t o = 0;
     auto carve = [&](size_t bytes) { size_t r = o; o += al(bytes); return r; };
