@@ -132,7 +132,10 @@ struct PassParams {
     uint32_t batch_tile;
 };
 
-__global__ void __launch_bounds__(512) k_ntt_pass(PassParams p) {
+#ifndef B2_NTT_MINBLOCKS
+#define B2_NTT_MINBLOCKS 2      // 64 registers: four 256-thread tiles per SM (76 registers uncapped = three)
+#endif
+__global__ void __launch_bounds__(512, B2_NTT_MINBLOCKS) k_ntt_pass(PassParams p) {
     extern __shared__ uint4 smem[];
     const uint32_t R = 1u << p.logR, G = 1u << p.logG;
     const uint32_t RG = R << p.logG;
@@ -163,29 +166,61 @@ __global__ void __launch_bounds__(512) k_ntt_pass(PassParams p) {
     }
     __syncthreads();
 
-    const uint32_t nbf = RG >> 1;
-    for (uint32_t s = 1; s <= p.logR; ++s) {
-        const uint32_t half = 1u << (s - 1);
+    // Butterfly stages, two at a time: a thread loads the four elements {e, e + h, e + 2h, e + 3h} of a radix-4 unit
+    // (h = 2^(s-1)), runs stage s on (e, e+h), (e+2h, e+3h) and stage s + 1 on (e, e+2h), (e+h, e+3h) in registers and
+    // stores them back: the same 4 twiddle products as two radix-2 stages (a prime field has no free multiplication by i),
+    // but one shared-memory round trip and one barrier instead of two, and four independent products in flight per thread.
+    // An odd number of stages starts with the single unit-twiddle stage s = 1.
+    auto lds = [&](uint32_t i) {
+        uint4 lo = s_lo[i], hi = s_hi[i];
+        Fr v;
+        v.l[0] = lo.x; v.l[1] = lo.y; v.l[2] = lo.z; v.l[3] = lo.w; v.l[4] = hi.x; v.l[5] = hi.y; v.l[6] = hi.z; v.l[7] = hi.w;
+        return v;
+    };
+    auto sts = [&](uint32_t i, const Fr& v) {
+        s_lo[i] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+        s_hi[i] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+    };
+    auto twd = [&](uint32_t ti) {
+        uint4 tl = s_tw[2 * ti], th = s_tw[2 * ti + 1];
+        Fr t;
+        t.l[0] = tl.x; t.l[1] = tl.y; t.l[2] = tl.z; t.l[3] = tl.w; t.l[4] = th.x; t.l[5] = th.y; t.l[6] = th.z; t.l[7] = th.w;
+        return t;
+    };
+    uint32_t s = 1;
+    if (p.logR & 1) {                       // stage 1 alone: (x, y) -> (x + y, x - y)
+        const uint32_t nbf = RG >> 1;
         for (uint32_t b = tid; b < nbf; b += nt) {
-            uint32_t c = b >> (p.logR - 1), bb = b & (R / 2 - 1);
-            uint32_t jj = bb & (half - 1);
-            uint32_t i0 = c * R + (((bb >> (s - 1)) << s) | jj), i1 = i0 + half;
-            uint4 ul = s_lo[i0], uh = s_hi[i0], vl = s_lo[i1], vh = s_hi[i1];
-            Fr u, v;
-            u.l[0] = ul.x; u.l[1] = ul.y; u.l[2] = ul.z; u.l[3] = ul.w; u.l[4] = uh.x; u.l[5] = uh.y; u.l[6] = uh.z; u.l[7] = uh.w;
-            v.l[0] = vl.x; v.l[1] = vl.y; v.l[2] = vl.z; v.l[3] = vl.w; v.l[4] = vh.x; v.l[5] = vh.y; v.l[6] = vh.z; v.l[7] = vh.w;
-            if (s > 1) {
-                uint32_t ti = jj << (p.logR - s);
-                uint4 tl = s_tw[2 * ti], th = s_tw[2 * ti + 1];
-                Fr t;
-                t.l[0] = tl.x; t.l[1] = tl.y; t.l[2] = tl.z; t.l[3] = tl.w; t.l[4] = th.x; t.l[5] = th.y; t.l[6] = th.z; t.l[7] = th.w;
-                v = Fr::mul(v, t);
+            const uint32_t c = b >> (p.logR - 1), bb = b & (R / 2 - 1);
+            const uint32_t i0 = c * R + (bb << 1), i1 = i0 + 1;
+            const Fr u = lds(i0), v = lds(i1);
+            sts(i0, Fr::add(u, v));
+            sts(i1, Fr::sub(u, v));
+        }
+        __syncthreads();
+        s = 2;
+    }
+    const uint32_t nq = RG >> 2;            // radix-4 units per tile
+    for (; s < p.logR + 1; s += 2) {        // stages s and s + 1 (logR - s + 1 is even here)
+        const uint32_t half = 1u << (s - 1);
+        for (uint32_t b = tid; b < nq; b += nt) {
+            const uint32_t c = b >> (p.logR - 2), bb = b & (R / 4 - 1);
+            const uint32_t jj = bb & (half - 1);
+            const uint32_t e0 = c * R + (((bb >> (s - 1)) << (s + 1)) | jj);
+            Fr x0 = lds(e0), x1 = lds(e0 + half), x2 = lds(e0 + 2 * half), x3 = lds(e0 + 3 * half);
+            if (s > 1) {                    // stage s twiddle w_R^(jj 2^(logR - s)), the same for both pairs
+                const Fr t = twd(jj << (p.logR - s));
+                x1 = Fr::mul(x1, t);
+                x3 = Fr::mul(x3, t);
             }
-            Fr x = Fr::add(u, v), y = Fr::sub(u, v);
-            s_lo[i0] = make_uint4(x.l[0], x.l[1], x.l[2], x.l[3]);
-            s_hi[i0] = make_uint4(x.l[4], x.l[5], x.l[6], x.l[7]);
-            s_lo[i1] = make_uint4(y.l[0], y.l[1], y.l[2], y.l[3]);
-            s_hi[i1] = make_uint4(y.l[4], y.l[5], y.l[6], y.l[7]);
+            Fr y0 = Fr::add(x0, x1), y1 = Fr::sub(x0, x1), y2 = Fr::add(x2, x3), y3 = Fr::sub(x2, x3);
+            // stage s + 1: pairs (y0, y2) at index jj and (y1, y3) at index jj + half of a 2^s-point group
+            y2 = Fr::mul(y2, twd(jj << (p.logR - s - 1)));
+            y3 = Fr::mul(y3, twd((jj + half) << (p.logR - s - 1)));
+            sts(e0, Fr::add(y0, y2));
+            sts(e0 + 2 * half, Fr::sub(y0, y2));
+            sts(e0 + half, Fr::add(y1, y3));
+            sts(e0 + 3 * half, Fr::sub(y1, y3));
         }
         __syncthreads();
     }
@@ -376,7 +411,10 @@ static int ntt_run(b200zk_ctx* ctx, Slot& sl, NttPlan* pl, const Fr* d_in, Fr* d
             p.p2p = 1; p.log_rl = p2p->log_rl; p.log_cols_total = p2p->log_cols_total; p.col0 = p2p->col0;
         }
         uint32_t RG = 1u << (p.logR + p.logG);
-        static const unsigned tdiv = getenv("B200ZK_NTT_TDIV") ? (unsigned)atoi(getenv("B200ZK_NTT_TDIV")) : 4;   // threads = tile / tdiv, tdiv / 2 butterflies per thread per stage (4: 1.013 ms vs 2: 1.111 ms at 2^22)
+        // threads = tile / tdiv: tdiv / 4 radix-4 units per thread per stage pair.  Measured after the stage pairing (round 2):
+        // 2^20 0.257 / 0.284 ms, 2^22 0.997 / 0.996 ms, 2^24 4.28 / 4.07 ms for tdiv = 4 / 8 -> 8 from 2^23 up
+        static const unsigned tdiv_env = getenv("B200ZK_NTT_TDIV") ? (unsigned)atoi(getenv("B200ZK_NTT_TDIV")) : 0;
+        const unsigned tdiv = tdiv_env ? tdiv_env : (pl->log_n >= 23 ? 8u : 4u);
         uint32_t threads = RG / tdiv < 32 ? 32 : RG / tdiv;
         size_t smem = (size_t)(2 * RG + (1u << p.logR)) * sizeof(uint4);
         dim3 grid((unsigned)(((size_t)1 << log_cols) >> p.logG), batch);
