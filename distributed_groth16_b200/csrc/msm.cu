@@ -572,36 +572,19 @@ struct MsmPart {
 template <class F>
 static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, const MsmPart* parts, unsigned nparts,
                         void* d_out, const char* acc_name, unsigned tab_c = 0, unsigned c_force = 0) {
-    const cudaStream_t st = ms.seq, ast = ms.acc;
     const int ch = ms.channel;
     size_t nev = 0;
     auto next_event = [&]() { return msm_event(ctx, ch, nev++); };
-    // inputs were produced in `result`-stream order
-    if (!ms.result_on_seq) {
-        cudaEvent_t e = next_event();
-        if (!e) return set_error(ctx, B200ZK_ERR_CUDA, "cudaEventCreate failed");
-        B2_CUDA_OK(ctx, cudaEventRecord(e, ast));
-        B2_CUDA_OK(ctx, cudaStreamWaitEvent(st, e, 0));
-    }
-    auto finish = [&]() -> int {          // the result (written on seq) becomes visible in result-stream order
-        if (!ms.result_on_seq) {
-            cudaEvent_t e = next_event();
-            if (!e) return set_error(ctx, B200ZK_ERR_CUDA, "cudaEventCreate failed");
-            B2_CUDA_OK(ctx, cudaEventRecord(e, st));
-            B2_CUDA_OK(ctx, cudaStreamWaitEvent(ast, e, 0));
-        }
-        return B200ZK_OK;
-    };
     size_t n = 0, n_max = 0;                                 // all parts together / the largest part
     for (unsigned p = 0; p < nparts; ++p) { n += parts[p].n; n_max = parts[p].n > n_max ? parts[p].n : n_max; }
     xyzz_t<F>* out = reinterpret_cast<xyzz_t<F>*>(d_out);
     if (n == 0) {
+        cudaStream_t rs = ms.result_on_seq ? ms.seq : ms.acc;
         {
-            LaunchScope ls(ctx, st, "msm_small");
-            k_set_identity<F><<<1, 32, 0, st>>>(out);
+            LaunchScope ls(ctx, rs, "msm_small");
+            k_set_identity<F><<<1, 32, 0, rs>>>(out);
         }
-        B2_TRY(check_launch(ctx, "k_set_identity"));
-        return finish();
+        return check_launch(ctx, "k_set_identity");
     }
     if (n >= (1ull << 31)) return set_error(ctx, B200ZK_ERR_ARG, "MSM length must be < 2^31");
     // tab_c != 0: the bases are a fixed-base table of msm_table_windows(tab_c) x n points (section 7); all digit windows
@@ -644,6 +627,29 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
     const unsigned units = (fold ? 1 : (glv ? Wh : W));
     auto group_first_unit = [&](unsigned g) { return (unsigned)(((uint64_t)units * g) / ngroups); };   // balanced split
     const uint32_t rmw = nparts > 1 ? 1u : 0u;               // bucket kernels add into the shared buckets
+
+    // Streams.  One group and one part (every MSM of a proof, the 2^20 benchmark point): nothing to overlap inside the MSM, so
+    // everything runs in order on the caller's stream as in round 1 -- a high-priority side stream would only let this MSM's
+    // reductions take SM time from the bucket kernels of the proof's other MSMs (measured: 18.5 -> 19.4 ms per 2^20 proof).
+    // Otherwise `seq` (side stream / lane stream) runs sort + tail and `acc` the bucket kernels.
+    const bool split_streams = ms.result_on_seq || ngroups > 1 || nparts > 1;
+    const cudaStream_t st = split_streams ? ms.seq : ms.acc, ast = ms.acc;
+    const bool handshake = split_streams && !ms.result_on_seq;
+    if (handshake) {                      // inputs were produced in `result`-stream order
+        cudaEvent_t e = next_event();
+        if (!e) return set_error(ctx, B200ZK_ERR_CUDA, "cudaEventCreate failed");
+        B2_CUDA_OK(ctx, cudaEventRecord(e, ast));
+        B2_CUDA_OK(ctx, cudaStreamWaitEvent(st, e, 0));
+    }
+    auto finish = [&]() -> int {          // the result (written on seq) becomes visible in result-stream order
+        if (handshake) {
+            cudaEvent_t e = next_event();
+            if (!e) return set_error(ctx, B200ZK_ERR_CUDA, "cudaEventCreate failed");
+            B2_CUDA_OK(ctx, cudaEventRecord(e, st));
+            B2_CUDA_OK(ctx, cudaStreamWaitEvent(ast, e, 0));
+        }
+        return B200ZK_OK;
+    };
 
     // workspace carve-up (256-byte aligned): the sort arrays once per part, the bucket set and the reduction buffers once
     auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
