@@ -275,10 +275,10 @@ __global__ void k_msm_task_order(const uint32_t* offsets, const uint32_t* task_o
 
 // G2 (Fq2 coordinates): 250 registers uncapped = 8 warps/SM, fmaheavy 74% busy with `wait` the top stall
 // (profiles/r1c_g2_accumulate.md); capped at 128 (4 blocks/SM, some spills) it measures 8.29 vs 8.89 ms at 2^20; 5+ blocks lose again
-template <class F>
+template <class F, bool RMW>
 __global__ void __launch_bounds__(128, sizeof(F) > 32 ? B2_ACC_MINBLOCKS_G2 : B2_ACC_MINBLOCKS) k_msm_accumulate(const affine_t<F>* bases, const uint32_t* entries, const uint32_t* offsets,
                                  const uint32_t* task_off, const uint32_t* task_bucket, const uint32_t* order,
-                                 uint32_t nbuckets, uint32_t task_len, uint32_t wave, uint32_t rmw, xyzz_t<F>* buckets, xyzz_t<F>* task_sums) {
+                                 uint32_t nbuckets, uint32_t task_len, uint32_t wave, xyzz_t<F>* buckets, xyzz_t<F>* task_sums) {
     // Block order over the length-sorted task list: the first `wave` blocks (one per resident slot) take an evenly
     // strided sample of the list, i.e. every length from the longest to the shortest, the others follow in descending
     // order.  In plain descending order each generation of resident blocks has equal lengths and ends at the same
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(128, sizeof(F) > 32 ? B2_ACC_MINBLOCKS_G2 : B2
     uint32_t hi = lo + task_len < end ? lo + task_len : end;
     // rmw (several input parts, msm_dev_impl): a single-task bucket continues from what the earlier parts left in it
     xyzz_t<F> acc = xyzz_t<F>::identity();
-    if (rmw && nt == 1) acc = ld16(buckets + g);
+    if (RMW && nt == 1) acc = ld16(buckets + g);
     for (uint32_t k = lo; k < hi; ++k) {
         uint32_t e = entries[k];
         affine_t<F> p = ld16(bases + (e & 0x7FFFFFFFu));
@@ -835,10 +835,13 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
             B2_CUDA_OK(ctx, cudaStreamWaitEvent(ast, prepped[(size_t)p * ngroups + g], 0));
             {
                 LaunchScope ls(ctx, ast, acc_name);
-                k_msm_accumulate<F><<<(unsigned)((G.task_cap + 127) / 128), 128, 0, ast>>>(
-                    reinterpret_cast<const affine_t<F>*>(P.bases), entries, offsets + G.b0, task_off_all + G.b0 + g, task_bucket_all + G.task_base,
-                    order_all + G.task_base, G.nbk, task_len, (uint32_t)ctx->sm_count * (sizeof(F) > 32 ? B2_ACC_MINBLOCKS_G2 : B2_ACC_MINBLOCKS),
-                    rmw, buckets + G.b0, task_sums_all + G.task_base);
+                const unsigned grid = (unsigned)((G.task_cap + 127) / 128);
+                const uint32_t wave = (uint32_t)ctx->sm_count * (sizeof(F) > 32 ? B2_ACC_MINBLOCKS_G2 : B2_ACC_MINBLOCKS);
+                const affine_t<F>* bp = reinterpret_cast<const affine_t<F>*>(P.bases);
+                if (rmw) k_msm_accumulate<F, true><<<grid, 128, 0, ast>>>(bp, entries, offsets + G.b0, task_off_all + G.b0 + g, task_bucket_all + G.task_base,
+                                                                       order_all + G.task_base, G.nbk, task_len, wave, buckets + G.b0, task_sums_all + G.task_base);
+                else k_msm_accumulate<F, false><<<grid, 128, 0, ast>>>(bp, entries, offsets + G.b0, task_off_all + G.b0 + g, task_bucket_all + G.task_base,
+                                                                        order_all + G.task_base, G.nbk, task_len, wave, buckets + G.b0, task_sums_all + G.task_base);
             }
             B2_TRY(check_launch(ctx, "k_msm_accumulate"));
             if (rmw) {

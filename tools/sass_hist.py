@@ -8,8 +8,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "distributed_groth16_b200", "libb200zk.so")
-KERNELS = [("k_msm_accumulate<Fq>  (G1 bucket kernel, dominant)", "k_msm_accumulateINS_2FpINS_8FqParams"),
-           ("k_msm_accumulate<Fq2> (G2 bucket kernel)", "k_msm_accumulateINS_3Fq2"),
+KERNELS = [("k_msm_accumulate<Fq>  (G1 bucket kernel, dominant)", "k_msm_accumulateINS_2FpINS_8FqParamsEEELb0"),
+           ("k_msm_accumulate<Fq2> (G2 bucket kernel)", "k_msm_accumulateINS_3Fq2ELb0"),
            ("k_ntt_pass", "k_ntt_pass"),
            ("k_msm_reduce_segments<Fq>", "k_msm_reduce_segmentsINS_2FpINS_8FqParams"),
            ("k_msm_exchange_sum<Fq> (fused peer exchange)", "k_msm_exchange_sumINS_2FpINS_8FqParams")]
