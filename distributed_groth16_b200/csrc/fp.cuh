@@ -246,7 +246,132 @@ struct Fp {
         ev[7] = cc::addc(ev[7], 0);
         Fp r; final_sub(r, ev); return r;
     }
-    B2_HD static Fp sqr(const Fp& a) { return mul(a, a); }
+#ifndef B2_SQR_VARIANT
+#define B2_SQR_VARIANT 1      // 1: dedicated squaring (36 + 72 wide multiply-adds instead of 136); 0: mul(a, a)
+#endif
+    B2_HD static Fp sqr(const Fp& a) {
+#if B2_SQR_VARIANT == 1
+        uint32_t t[16];
+        sqr_wide(t, a.l);
+        Fp r; redc<1>(r, t); return r;
+#else
+        return mul(a, a);
+#endif
+    }
+
+    // ---- unreduced 512-bit products and a separate Montgomery reduction ----------------------------------------------------
+    // Column-wise (product scanning) with a three-word column accumulator (c0, c1, c2): every partial product is one fused
+    // (mad.lo.cc, madc.hi.cc) pair = one wide multiply-add, plus an addc for the third word on the ALU pipe.  They exist for
+    // what the row-interleaved product above cannot do: squarings that compute each cross product once, and Fq2 products that
+    // reduce two sums of products instead of three products (Fq2::mul).
+    B2_HD static void col_mad(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t x, uint32_t y) {
+        c0 = cc::mad_lo_cc(x, y, c0);
+        c1 = cc::madc_hi_cc(x, y, c1);
+        c2 = cc::addc(c2, 0);
+    }
+    // t[0..16) = a * b
+    B2_HD static void mul_wide(uint32_t* t, const uint32_t* a, const uint32_t* b) {
+        uint32_t c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll
+        for (int k = 0; k < 15; ++k) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int j = k - i;
+                if (j >= 0 && j < 8) col_mad(c0, c1, c2, a[i], b[j]);
+            }
+            t[k] = c0; c0 = c1; c1 = c2; c2 = 0;
+        }
+        t[15] = c0;
+    }
+    // t[0..16) = a^2: the 28 cross products once, doubled, plus the 8 squares
+    B2_HD static void sqr_wide(uint32_t* t, const uint32_t* a) {
+        uint32_t c0 = 0, c1 = 0, c2 = 0;
+        t[0] = 0;
+#pragma unroll
+        for (int k = 1; k < 14; ++k) {                     // cross terms a_i a_j, i < j, i + j = k (k = 1 .. 13)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int j = k - i;
+                if (j > i && j < 8) col_mad(c0, c1, c2, a[i], a[j]);
+            }
+            t[k] = c0; c0 = c1; c1 = c2; c2 = 0;
+        }
+        t[14] = c0; t[15] = c1;                            // c1 = 0: the cross sum is < 2^(32 * 15)
+        // double (the sum of cross terms is < 2^511) and add the squares
+#pragma unroll
+        for (int k = 15; k > 0; --k) t[k] = (t[k] << 1) | (t[k - 1] >> 31);
+        t[0] = 0;
+        uint32_t carry = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint32_t lo = cc::mul_lo(a[i], a[i]), hi = cc::mul_hi(a[i], a[i]);
+            t[2 * i] = cc::add_cc(t[2 * i], carry);
+            t[2 * i + 1] = cc::addc_cc(t[2 * i + 1], 0);
+            carry = cc::addc(0, 0);
+            t[2 * i] = cc::add_cc(t[2 * i], lo);
+            t[2 * i + 1] = cc::addc_cc(t[2 * i + 1], hi);
+            carry = cc::addc(carry, 0);
+        }
+    }
+    // r = t / 2^256 mod p for t < SUBS * p * 2^256 (SUBS = 1: products of canonical values; 2: a lazy sum of two of them):
+    // column-wise Montgomery reduction, then SUBS conditional subtractions.  Clobbers nothing outside r.
+    template <int SUBS>
+    B2_HD static void redc(Fp& r, const uint32_t* t) {
+        uint32_t m[8], u[8];
+        uint32_t c0 = 0, c1 = 0, c2 = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int i = 0; i < k; ++i) col_mad(c0, c1, c2, m[i], P::mod(k - i));
+            c0 = cc::add_cc(c0, t[k]); c1 = cc::addc_cc(c1, 0); c2 = cc::addc(c2, 0);
+            m[k] = c0 * P::INV;
+            col_mad(c0, c1, c2, m[k], P::mod(0));           // c0 becomes 0
+            c0 = c1; c1 = c2; c2 = 0;
+        }
+#pragma unroll
+        for (int k = 8; k < 16; ++k) {
+#pragma unroll
+            for (int i = k - 7; i < 8; ++i) col_mad(c0, c1, c2, m[i], P::mod(k - i));
+            c0 = cc::add_cc(c0, t[k]); c1 = cc::addc_cc(c1, 0); c2 = cc::addc(c2, 0);
+            u[k - 8] = c0; c0 = c1; c1 = c2; c2 = 0;
+        }
+        // value = u + c0 * 2^256 < (SUBS + 1) p: subtract p while >= p (c0 can only be set when SUBS > 1)
+        uint32_t top = c0;
+#pragma unroll
+        for (int sidx = 0; sidx < SUBS; ++sidx) {
+            uint32_t d[8];
+            d[0] = cc::sub_cc(u[0], P::mod(0));
+#pragma unroll
+            for (int i = 1; i < 8; ++i) d[i] = cc::subc_cc(u[i], P::mod(i));
+            const uint32_t dtop = cc::subc(top, 0);
+            const bool ge = (int32_t)dtop >= 0;                 // no borrow out of the 288-bit subtraction
+#pragma unroll
+            for (int i = 0; i < 8; ++i) u[i] = ge ? d[i] : u[i];
+            top = ge ? dtop : top;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.l[i] = u[i];
+    }
+    // 512-bit helpers for lazy sums: x += y (no overflow by the callers' bounds), x -= y (x >= y)
+    B2_HD static void add_wide(uint32_t* x, const uint32_t* y) {
+        x[0] = cc::add_cc(x[0], y[0]);
+#pragma unroll
+        for (int i = 1; i < 15; ++i) x[i] = cc::addc_cc(x[i], y[i]);
+        x[15] = cc::addc(x[15], y[15]);
+    }
+    B2_HD static void sub_wide(uint32_t* x, const uint32_t* y) {
+        x[0] = cc::sub_cc(x[0], y[0]);
+#pragma unroll
+        for (int i = 1; i < 15; ++i) x[i] = cc::subc_cc(x[i], y[i]);
+        x[15] = cc::subc(x[15], y[15]);
+    }
+    // x += p * 2^256 (keeps a difference of two products non-negative)
+    B2_HD static void add_mod_hi(uint32_t* x) {
+        x[8] = cc::add_cc(x[8], P::mod(0));
+#pragma unroll
+        for (int i = 1; i < 7; ++i) x[8 + i] = cc::addc_cc(x[8 + i], P::mod(i));
+        x[15] = cc::addc(x[15], P::mod(7));
+    }
 
     // K independent products with their rows interleaved in program order.  One warp alone retires a single
     // product in ~0.42 us because each row waits on the previous one (carry chains + the m_i dependency);
@@ -385,13 +510,42 @@ struct Fq2 {
     B2_HD static Fq2 neg(const Fq2& a) { Fq2 r; r.c0 = Fq::neg(a.c0); r.c1 = Fq::neg(a.c1); return r; }
     B2_HD static Fq2 dbl(const Fq2& a) { return add(a, a); }
     // one out-of-line unit per Fq2 product (3 inlined Fq products): 10 calls per mixed add instead of 28
+#ifndef B2_FQ2_LAZY
+#define B2_FQ2_LAZY 1         // 1: three unreduced products, two reductions (336 wide multiply-adds); 0: three full products (384)
+#endif
     B2_HD_NI static Fq2 mul(const Fq2 a, const Fq2 b) {
+#if B2_FQ2_LAZY == 1
+        // c0 = a0 b0 - a1 b1, c1 = (a0 + a1)(b0 + b1) - a0 b0 - a1 b1, reduced once each.  Bounds: the products of canonical
+        // values are < p^2; sa, sb = a0 + a1, b0 + b1 < 2p (no reduction: < 2^255), so sa sb < 4 p^2 < 2^512 and
+        // c1's integer = a0 b1 + a1 b0 < 2 p^2 < 2 p 2^256; c0's = a0 b0 - a1 b1 + p 2^256 in (0, 2 p 2^256).
+        uint32_t t0[16], t1[16], t2[16], sa[8], sb[8];
+        Fq::mul_wide(t0, a.c0.l, b.c0.l);
+        Fq::mul_wide(t1, a.c1.l, b.c1.l);
+        sa[0] = cc::add_cc(a.c0.l[0], a.c1.l[0]);
+#pragma unroll
+        for (int i = 1; i < 7; ++i) sa[i] = cc::addc_cc(a.c0.l[i], a.c1.l[i]);
+        sa[7] = cc::addc(a.c0.l[7], a.c1.l[7]);
+        sb[0] = cc::add_cc(b.c0.l[0], b.c1.l[0]);
+#pragma unroll
+        for (int i = 1; i < 7; ++i) sb[i] = cc::addc_cc(b.c0.l[i], b.c1.l[i]);
+        sb[7] = cc::addc(b.c0.l[7], b.c1.l[7]);
+        Fq::mul_wide(t2, sa, sb);
+        Fq::sub_wide(t2, t0);
+        Fq::sub_wide(t2, t1);                                   // a0 b1 + a1 b0
+        Fq::add_mod_hi(t0);
+        Fq::sub_wide(t0, t1);                                   // a0 b0 - a1 b1 + p 2^256
+        Fq2 r;
+        Fq::template redc<2>(r.c0, t0);
+        Fq::template redc<2>(r.c1, t2);
+        return r;
+#else
         Fq v0 = Fq::mul(a.c0, b.c0), v1 = Fq::mul(a.c1, b.c1);
         Fq s = Fq::mul(Fq::add(a.c0, a.c1), Fq::add(b.c0, b.c1));
         Fq2 r;
         r.c0 = Fq::sub(v0, v1);
         r.c1 = Fq::sub(Fq::sub(s, v0), v1);
         return r;
+#endif
     }
     B2_HD_NI static Fq2 sqr(const Fq2 a) {
         Fq t = Fq::mul(Fq::add(a.c0, a.c1), Fq::sub(a.c0, a.c1));

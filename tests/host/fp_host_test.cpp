@@ -40,6 +40,11 @@ static int test_field(const char* name) {
         uint64_t exp[4];
         F r;
         r = F::mul(fa, fb); orc_field_op(FIELD, 0, a, b, exp); if (memcmp(r.l, exp, 32)) { fails++; if (fails < 5) printf("%s mul mismatch it=%d\n", name, it); }
+        { F sq = F::sqr(fa), mm = F::mul(fa, fa); if (sq != mm) { fails++; if (fails < 5) printf("%s sqr mismatch it=%d\n", name, it); } }
+        {   // unreduced product + separate reduction == the row-interleaved product
+            uint32_t t[16]; F::mul_wide(t, fa.l, fb.l); F w; F::template redc<1>(w, t);
+            if (w != F::mul(fa, fb)) { fails++; if (fails < 5) printf("%s mul_wide/redc mismatch it=%d\n", name, it); }
+        }
         r = F::add(fa, fb); orc_field_op(FIELD, 1, a, b, exp); if (memcmp(r.l, exp, 32)) { fails++; if (fails < 5) printf("%s add mismatch it=%d\n", name, it); }
         r = F::sub(fa, fb); orc_field_op(FIELD, 2, a, b, exp); if (memcmp(r.l, exp, 32)) { fails++; if (fails < 5) printf("%s sub mismatch it=%d\n", name, it); }
         if (it < 2000) {
@@ -246,6 +251,28 @@ static int test_batch_affine(const char* name, int is_g2) {
     return fails;
 }
 
+static int test_fq2_lazy_product() {
+    // Fq2::mul (three unreduced products, two reductions) vs the schoolbook formula on Fq, including the largest operands
+    int fails = 0;
+    Fq big = Fq::zero(); big.l[0] = 1; big = Fq::neg(big);          // p - 1
+    for (int it = 0; it < 5000; ++it) {
+        uint64_t buf[16];
+        orc_fr_generate(rnd(), 4, buf);
+        Fq2 a, b;
+        memcpy(a.c0.l, buf, 32); memcpy(a.c1.l, buf + 4, 32); memcpy(b.c0.l, buf + 8, 32); memcpy(b.c1.l, buf + 12, 32);
+        a.c0.l[7] &= 0x0FFFFFFFu; a.c1.l[7] &= 0x0FFFFFFFu; b.c0.l[7] &= 0x0FFFFFFFu; b.c1.l[7] &= 0x0FFFFFFFu;
+        if (it < 16) { if (it & 1) a.c0 = big; if (it & 2) a.c1 = big; if (it & 4) b.c0 = big; if (it & 8) b.c1 = big; }
+        if (it == 16) { a = Fq2::zero(); }
+        if (it == 17) { a.c0 = Fq::zero(); b.c1 = Fq::zero(); }
+        Fq2 got = Fq2::mul(a, b), want;
+        want.c0 = Fq::sub(Fq::mul(a.c0, b.c0), Fq::mul(a.c1, b.c1));
+        want.c1 = Fq::add(Fq::mul(a.c0, b.c1), Fq::mul(a.c1, b.c0));
+        if (!(got == want)) { if (fails++ < 5) printf("Fq2 lazy product mismatch it=%d\n", it); }
+    }
+    printf("Fq2 lazy-reduction product: %d failures\n", fails);
+    return fails;
+}
+
 int main() {
     int fails = 0;
     fails += test_field<Fq, 0>("Fq");
@@ -254,6 +281,7 @@ int main() {
     fails += test_curve<G2Curve>("G2", 1);
     fails += test_field29<FqParams, 0>("Fq");
     fails += test_field29<FrParams, 1>("Fr");
+    fails += test_fq2_lazy_product();
     fails += test_curve29();
     fails += test_batch_affine<G1Curve>("G1", 0);
     fails += test_batch_affine<G2Curve>("G2", 1);
