@@ -247,7 +247,7 @@ struct Fp {
         Fp r; final_sub(r, ev); return r;
     }
 #ifndef B2_SQR_VARIANT
-#define B2_SQR_VARIANT 1      // 1: dedicated squaring (36 + 72 wide multiply-adds instead of 136); 0: mul(a, a)
+#define B2_SQR_VARIANT 0      // 1: dedicated squaring (36 + 72 wide multiply-adds instead of 136) -- measured 3% SLOWER in the G1 bucket kernel (126 vs 120 registers, doubling shifts); 0: mul(a, a)
 #endif
     B2_HD static Fp sqr(const Fp& a) {
 #if B2_SQR_VARIANT == 1
