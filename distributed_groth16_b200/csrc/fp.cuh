@@ -249,6 +249,7 @@ struct Fp {
 #ifndef B2_SQR_VARIANT
 #define B2_SQR_VARIANT 0      // 1: dedicated squaring (36 + 72 wide multiply-adds instead of 136) -- measured 3% SLOWER in the G1 bucket kernel (126 vs 120 registers, doubling shifts); 0: mul(a, a)
 #endif
+    B2_HD static Fp sqr_inl(const Fp& a) { return sqr(a); }
     B2_HD static Fp sqr(const Fp& a) {
 #if B2_SQR_VARIANT == 1
         uint32_t t[16];
@@ -513,7 +514,9 @@ struct Fq2 {
 #ifndef B2_FQ2_LAZY
 #define B2_FQ2_LAZY 1         // 1: three unreduced products, two reductions (336 wide multiply-adds); 0: three full products (384)
 #endif
-    B2_HD_NI static Fq2 mul(const Fq2 a, const Fq2 b) {
+    B2_HD_NI static Fq2 mul(const Fq2 a, const Fq2 b) { return mul_inl(a, b); }
+    B2_HD_NI static Fq2 sqr(const Fq2 a) { return sqr_inl(a); }
+    B2_HD static Fq2 mul_inl(const Fq2& a, const Fq2& b) {
 #if B2_FQ2_LAZY == 1
         // c0 = a0 b0 - a1 b1, c1 = (a0 + a1)(b0 + b1) - a0 b0 - a1 b1, reduced once each.  Bounds: the products of canonical
         // values are < p^2; sa, sb = a0 + a1, b0 + b1 < 2p (no reduction: < 2^255), so sa sb < 4 p^2 < 2^512 and
@@ -547,7 +550,7 @@ struct Fq2 {
         return r;
 #endif
     }
-    B2_HD_NI static Fq2 sqr(const Fq2 a) {
+    B2_HD static Fq2 sqr_inl(const Fq2& a) {
         Fq t = Fq::mul(Fq::add(a.c0, a.c1), Fq::sub(a.c0, a.c1));
         Fq u = Fq::mul(a.c0, a.c1);
         Fq2 r; r.c0 = t; r.c1 = Fq::dbl(u); return r;

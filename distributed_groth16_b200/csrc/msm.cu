@@ -80,7 +80,7 @@ __global__ void k_msm_digits(const Fr* scalars, uint32_t n, uint32_t c, uint32_t
     }
 }
 
-// G1 only: k = k1 + k2 lambda (glv.cuh); window w of |k1| fills bucket set 2 (Wh - 1 - w), window w of |k2| set
+// k = k1 + k2 lambda (glv.cuh; G1 and, with beta^2, G2); window w of |k1| fills bucket set 2 (Wh - 1 - w), window w of |k2| set
 // 2 (Wh - 1 - w) + 1 over the same points (top windows first, the two halves interleaved: see k_msm_digits) -- phi is
 // applied once to the second chain's result in k_msm_horner_glv.
 __global__ void k_msm_digits_glv(const Fr* scalars, uint32_t n, uint32_t c, uint32_t Wh, uint32_t* keys, uint32_t* ranks,
@@ -439,15 +439,30 @@ __global__ void __launch_bounds__(32) k_msm_horner(const xyzz_t<F>* wsum, uint32
 }
 
 // GLV variant: quad 0 runs the chain of the |k1| windows (sets 2k), quad 1 that of the |k2| windows (sets 2k + 1) in
-// the same warp (half as many sequential doublings); result = H0 + phi(H1), phi(X, Y, ZZ, ZZZ) = (beta X, Y, ZZ, ZZZ).
-__global__ void __launch_bounds__(32) k_msm_horner_glv(const xyzz_t<Fq>* wsum, uint32_t nwin, uint32_t c, uint32_t first, uint32_t last,
-                                                       xyzz_t<Fq>* state, xyzz_t<Fq>* out) {
-    typedef quad_ops<Fq, false> Q;
-    __shared__ Q::xch_t xch[2];
-    __shared__ xyzz_t<Fq> h1;
+// the same warp (half as many sequential doublings); result = H0 + phi(H1), phi(X, Y, ZZ, ZZZ) = (beta X, Y, ZZ, ZZZ) on G1 and
+// (beta^2 X, Y, ZZ, ZZZ) on the twist (the same lambda: tools/gen_constants.py checks both).
+__device__ __forceinline__ void glv_phi_x(Fq& x) {
+    Fq beta;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) beta.l[i] = GlvParams::beta(i);
+    x = Fq::mul(x, beta);
+}
+__device__ __forceinline__ void glv_phi_x(Fq2& x) {
+    Fq beta;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) beta.l[i] = GlvParams::beta_g2(i);
+    x.c0 = Fq::mul(x.c0, beta);
+    x.c1 = Fq::mul(x.c1, beta);
+}
+template <class F>
+__global__ void __launch_bounds__(32) k_msm_horner_glv(const xyzz_t<F>* wsum, uint32_t nwin, uint32_t c, uint32_t first, uint32_t last,
+                                                       xyzz_t<F>* state, xyzz_t<F>* out) {
+    typedef quad_ops<F, false> Q;
+    __shared__ typename Q::xch_t xch[2];
+    __shared__ xyzz_t<F> h1;
     if (blockIdx.x != 0 || threadIdx.x >= 8) return;
     const uint32_t half = threadIdx.x >> 2;
-    xyzz_t<Fq> total;
+    xyzz_t<F> total;
     uint32_t k = 0;
     if (first) { total = ld16(wsum + half); k = 1; }
     else total = ld16(state + half);
@@ -462,11 +477,8 @@ __global__ void __launch_bounds__(32) k_msm_horner_glv(const xyzz_t<Fq>* wsum, u
     if (threadIdx.x == 4) h1 = total;
     __syncwarp(0xFFu);
     if (half == 0) {
-        xyzz_t<Fq> p = h1;
-        Fq beta;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) beta.l[i] = GlvParams::beta(i);
-        if (!p.is_inf()) p.x = Fq::mul(p.x, beta);
+        xyzz_t<F> p = h1;
+        if (!p.is_inf()) glv_phi_x(p.x);
         total = Q::add(&xch[0], total, p);
         if (threadIdx.x == 0) st16(out, total);
     }
@@ -593,7 +605,8 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
     if (fold && nparts != 1) return set_error(ctx, B200ZK_ERR_ARG, "fixed-base tables take one input part");
     const unsigned c = fold ? tab_c : (c_force ? c_force : choose_window(n));
     static const bool glv_env = !(getenv("B200ZK_MSM_GLV") && getenv("B200ZK_MSM_GLV")[0] == '0');
-    const bool glv = !fold && glv_env && sizeof(F) == 32;    // G1 only (glv.cuh)
+    static const bool glv2_env = !(getenv("B200ZK_MSM_GLV_G2") && getenv("B200ZK_MSM_GLV_G2")[0] == '0');
+    const bool glv = !fold && glv_env && (sizeof(F) == 32 || glv2_env);   // glv.cuh; G2: the same split, phi = (beta^2 x, y)
     const unsigned Wh = (128 + c - 1) / c;                   // |k1|, |k2| < 2^127: Wh * c >= 128 leaves the carry room
     const unsigned W = glv ? 2 * Wh : (255 + c - 1) / c;     // digit windows
     const unsigned WB = fold ? 1 : W;                        // bucket sets
@@ -905,8 +918,7 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
         {
             LaunchScope ls(ctx, st, "msm_combine");
             const uint32_t first = g == 0, last = g + 1 == ngroups;
-            if (glv) k_msm_horner_glv<<<1, 32, 0, st>>>(reinterpret_cast<const xyzz_t<Fq>*>(wsum) + G.set0, G.nsets / 2, c, first, last,
-                                                        reinterpret_cast<xyzz_t<Fq>*>(hstate), reinterpret_cast<xyzz_t<Fq>*>(out));
+            if (glv) k_msm_horner_glv<F><<<1, 32, 0, st>>>(wsum + G.set0, G.nsets / 2, c, first, last, hstate, out);
             else k_msm_horner<F><<<1, 32, 0, st>>>(wsum + (size_t)G.set0 * wsplit, G.nsets * wsplit, fold ? 0u : c, first, last, hstate, out);
         }
         B2_TRY(check_launch(ctx, "k_msm_horner"));

@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(512, B2_NTT_MINBLOCKS) k_ntt_pass(PassParams p
             }
             Fr y0 = Fr::add(x0, x1), y1 = Fr::sub(x0, x1), y2 = Fr::add(x2, x3), y3 = Fr::sub(x2, x3);
             // stage s + 1: pairs (y0, y2) at index jj and (y1, y3) at index jj + half of a 2^s-point group
-            y2 = Fr::mul(y2, twd(jj << (p.logR - s - 1)));
+            if (s > 1) y2 = Fr::mul(y2, twd(jj << (p.logR - s - 1)));      // s = 1: jj = 0, unit twiddle
             y3 = Fr::mul(y3, twd((jj + half) << (p.logR - s - 1)));
             sts(e0, Fr::add(y0, y2));
             sts(e0 + 2 * half, Fr::sub(y0, y2));
@@ -321,7 +321,12 @@ static int get_plan(b200zk_ctx* ctx, cudaStream_t st, unsigned log_n, bool inver
         for (unsigned i = 0; i < pl->npass; ++i) {
             pl->has_tw_pass[i] = false;
             unsigned range = log_n - logL;                      // exponents n'' k_s < N / L
-            if (i > 0 && i + 1 < pl->npass && range <= 16) {
+            // first boundary (range = log_n): one table of N entries (128 MB at 2^22) read once per transform -- 32 B gathers the
+            // otherwise idle HBM serves -- instead of a second product through the two-level table; B200ZK_NTT_BIGTAB = largest
+            // log_n that gets one (default 24: 512 MB per direction), 0 = never
+            static const unsigned bigtab = getenv("B200ZK_NTT_BIGTAB") ? (unsigned)atoi(getenv("B200ZK_NTT_BIGTAB")) : 24u;
+            const bool first_big = i == 0 && pl->npass > 1 && range > 16 && range <= bigtab;
+            if ((i > 0 && i + 1 < pl->npass && range <= 16) || first_big) {
                 Fr* t = nullptr;
                 B2_CUDA_OK(ctx, cudaMalloc(&t, sizeof(Fr) << range));
                 pl->allocs.push_back(t);

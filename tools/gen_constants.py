@@ -95,6 +95,10 @@ def glv_constants():
     assert a1 > 0 and b1 < 0 and a2 > 0 and b2 > 0, (a1, b1, a2, b2)
     g1 = ((1 << 256) * b2) // r
     g2 = ((1 << 256) * (-b1)) // r
+    # G2: lambda Q = (beta^2 x, y) for Q on the twist
+    Q = o.G2.mul(o.G2_GEN, 0xB200)
+    b2sq = beta * beta % o.P
+    assert o.G2.mul(Q, lam) == ((Q[0][0] * b2sq % o.P, Q[0][1] * b2sq % o.P), Q[1])
     return dict(lam=lam, beta=beta, a1=a1, nb1=-b1, a2=a2, b2=b2, g1=g1, g2=g2)
 
 
@@ -102,6 +106,8 @@ def glv_params():
     g = glv_constants()
     s = "struct GlvParams {\n"
     s += arr("beta", limbs32(o.fq_mont(g["beta"])))          # Fq, Montgomery
+    # on the twist E'(Fq2) the same lambda acts as (x, y) -> (beta^2 x, y) (checked in glv_constants)
+    s += arr("beta_g2", limbs32(o.fq_mont(g["beta"] * g["beta"] % o.P)))
     s += arr("lambda_mont", limbs32(o.fr_mont(g["lam"])))    # Fr, Montgomery (tests)
     s += arr("a1", limbs32(g["a1"], 2))
     s += arr("nb1", limbs32(g["nb1"], 4))                    # -b1 > 0
