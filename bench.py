@@ -140,14 +140,17 @@ def measure_ntt(net, hbm_peak, pipe_peak):
     ms = sum(ts) / len(ts)
     back = torch.empty_like(x)
     net.ntt_dev(y, back, inverse=True)
-    # products per element, as csrc/ntt.cu runs it: passes of <= 8 butterfly levels whose first level has unit twiddles, and at
-    # every pass boundary the inter-pass twiddle: 2 products through the two-level power table, 1 where a single-level table
-    # exists (middle passes with <= 2^16 distinct exponents)
+    # products per element, as csrc/ntt.cu runs it: passes of <= 8 butterfly levels whose first level has unit twiddles (and, in a
+    # pass with an even number of levels, half of the second level too: the first radix-4 unit multiplies by 1 and i only), and
+    # at every pass boundary the inter-pass twiddle: 1 product where a single-level table exists (first boundary up to 2^24,
+    # middle passes with <= 2^16 distinct exponents), 2 through the two-level power table otherwise
     passes = -(-log_n // 8)
     log_r = [log_n // passes + (1 if i < log_n % passes else 0) for i in range(passes)]
-    per_elem, log_l = (log_n - passes) / 2.0, 0
+    per_elem, log_l = (log_n - passes) / 2.0 - 0.25 * sum(1 for r in log_r if r % 2 == 0), 0
+    bigtab = int(os.environ.get("B200ZK_NTT_BIGTAB", "24"))
     for i in range(passes - 1):
-        per_elem += 1.0 if (i > 0 and log_n - log_l <= 16) else 2.0
+        single = (i == 0 and log_n <= bigtab) or (i > 0 and log_n - log_l <= 16)
+        per_elem += 1.0 if single else 2.0
         log_l += log_r[i]
     products = n * per_elem
     return {"metric": "Fr NTT 2^%d (BN254 scalar field)" % log_n, "ms": ms, "ms_min": ts[0], "gelem_s": n / ms / 1e6,
@@ -156,8 +159,8 @@ def measure_ntt(net, hbm_peak, pipe_peak):
                          "pipe": {"achieved": products / ms / 1e6, "peak": pipe_peak, "unit": "G modular products/s",
                                   "frac": products / ms / 1e6 / pipe_peak,
                                   "products_per_element": per_elem,
-                                  "how": "n x ((log n - passes) / 2 butterfly products + 2 (two-level table) or 1 (single-level) twiddle "
-                                         "products per pass boundary)"}},
+                                  "how": "n x ((log n - passes) / 2 butterfly products - 1/4 per pass with an even number of levels + 1 "
+                                         "(single-level table) or 2 (two-level) twiddle products per pass boundary)"}},
             "round_trip_exact": bool((back == x).all()),
             "timing": "CUDA events per transform, L2 flushed between transforms, 10 runs after 3 warm-ups"}
 

@@ -39,6 +39,7 @@ struct NttPlan {
     bool has_tw_pass[8];
     PowTab coset;        // powers of consts[2]   (lazy)
     PowTab shift;        // powers of consts[3]   (lazy; used by h)
+    bool scale_folded = false;   // inverse plans: tw_pass[0] carries the 1/N of the inverse transform
     std::vector<void*> allocs;
 };
 
@@ -98,11 +99,13 @@ __global__ void k_plan_consts(unsigned log_n, int inverse, Fr* consts) {
     consts[3] = w2;
 }
 
-// out[i] = base^(i << shift)
-__global__ void k_build_pow(const Fr* base_ptr, Fr* out, uint32_t count, uint32_t shift) {
+// out[i] = base^(i << shift) (* scale, if given)
+__global__ void k_build_pow(const Fr* base_ptr, Fr* out, uint32_t count, uint32_t shift, const Fr* scale = nullptr) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
-    st_fr(out + i, fr_pow_u64(*base_ptr, (uint64_t)i << shift));
+    Fr v = fr_pow_u64(*base_ptr, (uint64_t)i << shift);
+    if (scale) v = Fr::mul(v, *scale);
+    st_fr(out + i, v);
 }
 
 struct PassParams {
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(512, B2_NTT_MINBLOCKS) k_ntt_pass(PassParams p
         v.l[0] = a.x; v.l[1] = a.y; v.l[2] = a.z; v.l[3] = a.w; v.l[4] = bq.x; v.l[5] = bq.y; v.l[6] = bq.z; v.l[7] = bq.w;
         if (p.apply_tw) {
             uint64_t ex = (n2 * ks) << p.tw_shift;
-            if (ex) v = Fr::mul(v, powtab_get(p.tw, ex));
+            if (ex || p.apply_tw == 2) v = Fr::mul(v, powtab_get(p.tw, ex));
         }
         uint64_t oaddr = ((j + ((uint64_t)ks << p.logL)) << p.logM) + n2;
         if (p.apply_post) {
@@ -322,10 +325,11 @@ static int get_plan(b200zk_ctx* ctx, cudaStream_t st, unsigned log_n, bool inver
             pl->has_tw_pass[i] = false;
             unsigned range = log_n - logL;                      // exponents n'' k_s < N / L
             // first boundary (range = log_n): one table of N entries (128 MB at 2^22) read once per transform -- 32 B gathers the
-            // otherwise idle HBM serves -- instead of a second product through the two-level table; B200ZK_NTT_BIGTAB = largest
-            // log_n that gets one (default 24: 512 MB per direction), 0 = never
+            // otherwise idle HBM serves -- instead of a second product through the two-level table; an inverse plan's table also
+            // carries the 1/N every inverse transform ends with.  B200ZK_NTT_BIGTAB = largest log_n that gets one (default 24:
+            // 512 MB per direction), 0 = never
             static const unsigned bigtab = getenv("B200ZK_NTT_BIGTAB") ? (unsigned)atoi(getenv("B200ZK_NTT_BIGTAB")) : 24u;
-            const bool first_big = i == 0 && pl->npass > 1 && range > 16 && range <= bigtab;
+            const bool first_big = i == 0 && pl->npass > 1 && range <= bigtab;
             if ((i > 0 && i + 1 < pl->npass && range <= 16) || first_big) {
                 Fr* t = nullptr;
                 B2_CUDA_OK(ctx, cudaMalloc(&t, sizeof(Fr) << range));
@@ -333,7 +337,9 @@ static int get_plan(b200zk_ctx* ctx, cudaStream_t st, unsigned log_n, bool inver
                 {
                     LaunchScope ls(ctx, st, "ntt_build_tables");
                     uint32_t cnt = 1u << range;
-                    k_build_pow<<<(cnt + 127) / 128, 128, 0, st>>>(pl->consts, t, cnt, logL);
+                    const bool fold_scale = first_big && inverse;
+                    k_build_pow<<<(cnt + 127) / 128, 128, 0, st>>>(pl->consts, t, cnt, logL, fold_scale ? pl->consts + 1 : nullptr);
+                    if (fold_scale) pl->scale_folded = true;
                 }
                 B2_TRY(check_launch(ctx, "k_build_pow(tw_pass)"));
                 pl->tw_pass[i].lo = t; pl->tw_pass[i].hi = t; pl->tw_pass[i].lo_bits = range;
@@ -353,7 +359,22 @@ static int plan_lazy_tab(b200zk_ctx* ctx, cudaStream_t st, NttPlan* pl, int whic
     std::lock_guard<std::mutex> g(ctx->plan_mu);
     PowTab* t = which == 2 ? &pl->coset : &pl->shift;
     if (!t->lo) {
-        B2_TRY(build_powtab(ctx, st, pl, pl->consts + which, pl->log_n, t));
+        // exponents < N.  One level (one product per element instead of two) up to B200ZK_NTT_BIGTAB, like the first pass boundary
+        static const unsigned bigtab = getenv("B200ZK_NTT_BIGTAB") ? (unsigned)atoi(getenv("B200ZK_NTT_BIGTAB")) : 24u;
+        if (pl->log_n <= bigtab) {
+            Fr* tab = nullptr;
+            B2_CUDA_OK(ctx, cudaMalloc(&tab, sizeof(Fr) << pl->log_n));
+            pl->allocs.push_back(tab);
+            {
+                LaunchScope ls(ctx, st, "ntt_build_tables");
+                uint32_t cnt = 1u << pl->log_n;
+                k_build_pow<<<(cnt + 127) / 128, 128, 0, st>>>(pl->consts + which, tab, cnt, 0);
+            }
+            B2_TRY(check_launch(ctx, "k_build_pow(lazy)"));
+            t->hi = tab; t->lo_bits = pl->log_n; t->lo = tab;
+        } else {
+            B2_TRY(build_powtab(ctx, st, pl, pl->consts + which, pl->log_n, t));
+        }
         B2_CUDA_OK(ctx, cudaStreamSynchronize(st));
     }
     *out = t;
@@ -403,13 +424,13 @@ static int ntt_run(b200zk_ctx* ctx, Slot& sl, NttPlan* pl, const Fr* d_in, Fr* d
         p.tw = pl->tw;
         p.tw_shift = logL;
         if (pl->has_tw_pass[i]) { p.tw = pl->tw_pass[i]; p.tw_shift = 0; }
-        p.apply_tw = last ? 0 : 1;
+        p.apply_tw = last ? 0 : (i == 0 && pl->scale_folded ? 2 : 1);          // 2: the table entry for exponent 0 is 1/N, not 1
         if (i == 0 && pre) { p.pre = *pre; p.apply_pre = 1; }
         if (last && post) {
             p.post = *post; p.apply_post = 1;
             p.post_b0 = pe.b0; p.post_alpha = pe.alpha; p.post_beta = pe.beta; p.post_gamma = pe.gamma;
         }
-        if (last && post_const) { p.post_const = post_const; p.apply_post_const = 1; }
+        if (last && post_const && !pl->scale_folded) { p.post_const = post_const; p.apply_post_const = 1; }
         p.batch_stride = N;
         if (last && p2p) {
             for (unsigned g = 0; g < 8; ++g) p.peer_out[g] = g < p2p->n_peers ? p2p->peer[g] : nullptr;
