@@ -8,6 +8,8 @@
 #include "../../distributed_groth16_b200/csrc/ec.cuh"
 #include "../../tools/experiments/ec29.cuh"
 #include "../../tools/experiments/batch_affine.cuh"
+#include "../../tools/experiments/fp52.cuh"
+#include <cfenv>
 
 extern "C" void orc_field_op(int field, int op, const uint64_t* a, const uint64_t* b, uint64_t* out);
 extern "C" void orc_fr_generate(uint64_t seed, size_t n, uint64_t* out);
@@ -273,8 +275,40 @@ static int test_fq2_lazy_product() {
     return fails;
 }
 
+// ---- fp52.cuh: 5 x 52-bit limbs, products from pairs of round-towards-zero FMAs -------------------------------------------
+template <class P, int FIELD>
+static int test_field52(const char* name) {
+    typedef Fp<P> F;
+    typedef Fp52<P> G;
+    int fails = 0;
+    const int N = 20000;
+    const int old = fegetround();
+    fesetround(FE_TOWARDZERO);
+    for (int it = 0; it < N; ++it) {
+        uint64_t buf[8];
+        orc_fr_generate(rnd(), 2, buf);
+        F a, b; memcpy(a.l, buf, 32); memcpy(b.l, buf + 4, 32);
+        if (FIELD == 0) { a.l[7] &= 0x0FFFFFFFu; b.l[7] &= 0x0FFFFFFFu; }
+        if (it == 0) a = F::zero();
+        if (it == 1) b = F::zero();
+        if (it == 2) { a = F::neg(F::one()); b = a; }
+        if (it == 3) { a = F::zero(); a.l[0] = 1; a = F::neg(a); b = a; }   // p - 1, the largest canonical integer
+        G ga = G::from_mont256(a), gb = G::from_mont256(b);
+        F r = G::to_mont256(G::mul(ga, gb));
+        if (r != F::mul(a, b)) { if (fails++ < 5) printf("%s mul52 mismatch it=%d\n", name, it); }
+        // a chain: ((a b) a) b
+        r = G::to_mont256(G::mul(G::mul(G::mul(ga, gb), ga), gb));
+        if (r != F::mul(F::mul(F::mul(a, b), a), b)) { if (fails++ < 5) printf("%s mul52 chain mismatch it=%d\n", name, it); }
+    }
+    fesetround(old);
+    printf("%s (52-bit limbs, FMA products): %d iterations, %d failures\n", name, N, fails);
+    return fails;
+}
+
 int main() {
     int fails = 0;
+    fails += test_field52<FqParams, 0>("Fq");
+    fails += test_field52<FrParams, 1>("Fr");
     fails += test_field<Fq, 0>("Fq");
     fails += test_field<Fr, 1>("Fr");
     fails += test_curve<G1Curve>("G1", 0);

@@ -22,7 +22,7 @@ def test_device_limb_schedule_on_host(cref, tmp_path):
     """csrc/fp.cuh + ec.cuh compiled for the host (PTX carry primitives emulated) vs the oracle."""
     exe = tmp_path / "fp_host_test"
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    subprocess.check_call([cxx, "-O2", "-std=c++17", "-o", str(exe), os.path.join(ROOT, "tests", "host", "fp_host_test.cpp"),
+    subprocess.check_call([cxx, "-O2", "-std=c++17", "-frounding-math", "-o", str(exe), os.path.join(ROOT, "tests", "host", "fp_host_test.cpp"),
                            "-L" + os.path.join(ROOT, "oracle"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle"),
                            "-fopenmp"])
     out = subprocess.run([str(exe)], capture_output=True, text=True)
