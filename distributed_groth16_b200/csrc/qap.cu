@@ -52,6 +52,40 @@ __global__ void k_qap(const uint32_t* a_ptr, const uint32_t* a_col, const Fr* a_
     stq(a + i, va); stq(b + i, vb); stq(c + i, vc);
 }
 
+// One warp per row: the lanes stride over the row's non-zeros and the partial sums meet in a shuffle tree.  Small circuits have
+// far fewer rows than the machine has lanes and a few long rows (the reference's sha256 circuit: 30 134 rows, the longest row
+// is a serial chain of ~0.5 ms for one thread); field addition is exact, so the order of summation does not change the result.
+__device__ __forceinline__ Fr warp_sum(Fr v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        Fr o;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.l[i] = __shfl_down_sync(0xFFFFFFFFu, v.l[i], d);
+        v = Fr::add(v, o);
+    }
+    return v;
+}
+__device__ __forceinline__ Fr row_dot_warp(const uint32_t* ptr, const uint32_t* col, const Fr* val, const Fr* z, uint32_t i, uint32_t lane) {
+    Fr acc = Fr::zero();
+    for (uint32_t k = ptr[i] + lane, e = ptr[i + 1]; k < e; k += 32) acc = Fr::add(acc, Fr::mul(ldq(val + k), ldq(z + col[k])));
+    return warp_sum(acc);
+}
+__global__ void __launch_bounds__(256) k_qap_warp(const uint32_t* a_ptr, const uint32_t* a_col, const Fr* a_val, const uint32_t* b_ptr,
+                                                  const uint32_t* b_col, const Fr* b_val, const Fr* z, uint32_t nc, uint32_t n_inputs,
+                                                  uint32_t m, Fr* a, Fr* b, Fr* c) {
+    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= m) return;
+    Fr va = Fr::zero(), vb = Fr::zero(), vc = Fr::zero();
+    if (i < nc) {
+        va = row_dot_warp(a_ptr, a_col, a_val, z, i, lane);
+        vb = row_dot_warp(b_ptr, b_col, b_val, z, i, lane);
+        vc = Fr::mul(va, vb);
+    } else if (i < nc + n_inputs) {
+        va = ldq(z + (i - nc));
+    }
+    if (lane == 0) { stq(a + i, va); stq(b + i, vb); stq(c + i, vc); }
+}
+
 int fr_convert_dev(b200zk_ctx* ctx, Slot& sl, const void* d_in, void* d_out, size_t n, int to_mont, int times) {
     if (n == 0) return B200ZK_OK;
     {
@@ -69,10 +103,13 @@ int qap_dev(b200zk_ctx* ctx, Slot& sl, const void* a_ptr, const void* a_col, con
     if (nc + n_inputs > m) return set_error(ctx, B200ZK_ERR_DOMAIN, "num_constraints + num_inputs exceeds the domain size");
     {
         LaunchScope ls(ctx, sl.stream, "qap_matvec");
-        k_qap<<<(unsigned)((m + 127) / 128), 128, 0, sl.stream>>>((const uint32_t*)a_ptr, (const uint32_t*)a_col, (const Fr*)a_val,
-                                                                   (const uint32_t*)b_ptr, (const uint32_t*)b_col, (const Fr*)b_val,
-                                                                   (const Fr*)d_z, (uint32_t)nc, (uint32_t)n_inputs, (uint32_t)m,
-                                                                   (Fr*)d_a, (Fr*)d_b, (Fr*)d_c);
+        const uint32_t *ap = (const uint32_t*)a_ptr, *ac = (const uint32_t*)a_col, *bp = (const uint32_t*)b_ptr, *bc = (const uint32_t*)b_col;
+        if (m <= ((size_t)1 << 18))          // warp per row while rows x 32 lanes still fit a few waves
+            k_qap_warp<<<(unsigned)((m * 32 + 255) / 256), 256, 0, sl.stream>>>(ap, ac, (const Fr*)a_val, bp, bc, (const Fr*)b_val, (const Fr*)d_z,
+                                                                                (uint32_t)nc, (uint32_t)n_inputs, (uint32_t)m, (Fr*)d_a, (Fr*)d_b, (Fr*)d_c);
+        else
+            k_qap<<<(unsigned)((m + 127) / 128), 128, 0, sl.stream>>>(ap, ac, (const Fr*)a_val, bp, bc, (const Fr*)b_val, (const Fr*)d_z,
+                                                                       (uint32_t)nc, (uint32_t)n_inputs, (uint32_t)m, (Fr*)d_a, (Fr*)d_b, (Fr*)d_c);
     }
     return check_launch(ctx, "k_qap");
 }

@@ -13,7 +13,35 @@ from distributed_groth16_b200._constants import FR_ONE_MONT  # noqa: E402
 from distributed_groth16_b200.groth16 import ProvingKey, prove  # noqa: E402
 
 
+def sha256():
+    """the reference's sha256 circuit (config 4): every launch >= 5 us"""
+    from distributed_groth16_b200.groth16 import circom, setup
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden", "sha256_circuit.npz"))
+    n_wires, n_pub, n_cons = (int(x) for x in d["dims"])
+    coo = lambda k: (d[k + "_rows"], d[k + "_cols"], d[k + "_vals"])
+    net = Net(0)
+    net.use_torch_stream(0)
+    pk, vk, mats = setup.circuit_specific_setup(net, n_wires, n_pub + 1, n_cons, coo("a"), coo("b"), coo("c"),
+                                                (0x1234567, 0x2345678, 0x3456789, 0x456789A, 0x56789AB))
+    z = net.fr_convert(net.to_device(d["witness"]), to_mont=True)
+    zero = np.zeros(4, dtype=np.uint64)
+    for _ in range(3):
+        circom.prove_from_matrices(pk, mats, z, zero, zero)
+    net.profile(True)
+    net.profile_reset()
+    circom.prove_from_matrices(pk, mats, z, zero, zero)
+    rep = net.profile_report()
+    net.profile(False)
+    tl = sorted(rep.pop("_timeline"), key=lambda t: t[1])
+    print("profiled sha256 prove: %.2f ms, %d launches" % (max(t[2] for t in tl), len(tl)))
+    for name, t0, t1 in tl:
+        if t1 - t0 >= 0.005:
+            print("%8.3f %8.3f  %7.3f  %s" % (t0, t1, t1 - t0, name))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "sha256":
+        return sha256()
     log_m = int(sys.argv[1]) if len(sys.argv) > 1 else 20
     m = 1 << log_m
     n_vars, n_inputs = m, 2
