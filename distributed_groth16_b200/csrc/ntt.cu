@@ -332,7 +332,12 @@ static int get_plan(b200zk_ctx* ctx, cudaStream_t st, unsigned log_n, bool inver
             const bool first_big = i == 0 && pl->npass > 1 && range <= bigtab;
             if ((i > 0 && i + 1 < pl->npass && range <= 16) || first_big) {
                 Fr* t = nullptr;
-                B2_CUDA_OK(ctx, cudaMalloc(&t, sizeof(Fr) << range));
+                if (cudaMalloc(&t, sizeof(Fr) << range) != cudaSuccess) {
+                    cudaGetLastError();
+                    if (!first_big) return set_error(ctx, B200ZK_ERR_OOM, "cudaMalloc failed for an NTT twiddle table");
+                    logL += pl->logR[i];                        // no room for the big table: the two-level one serves this boundary
+                    continue;
+                }
                 pl->allocs.push_back(t);
                 {
                     LaunchScope ls(ctx, st, "ntt_build_tables");
@@ -361,9 +366,9 @@ static int plan_lazy_tab(b200zk_ctx* ctx, cudaStream_t st, NttPlan* pl, int whic
     if (!t->lo) {
         // exponents < N.  One level (one product per element instead of two) up to B200ZK_NTT_BIGTAB, like the first pass boundary
         static const unsigned bigtab = getenv("B200ZK_NTT_BIGTAB") ? (unsigned)atoi(getenv("B200ZK_NTT_BIGTAB")) : 24u;
-        if (pl->log_n <= bigtab) {
-            Fr* tab = nullptr;
-            B2_CUDA_OK(ctx, cudaMalloc(&tab, sizeof(Fr) << pl->log_n));
+        Fr* tab = nullptr;
+        if (pl->log_n <= bigtab && cudaMalloc(&tab, sizeof(Fr) << pl->log_n) != cudaSuccess) { cudaGetLastError(); tab = nullptr; }
+        if (tab) {
             pl->allocs.push_back(tab);
             {
                 LaunchScope ls(ctx, st, "ntt_build_tables");
