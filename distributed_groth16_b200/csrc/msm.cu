@@ -671,7 +671,26 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
     }
     const unsigned unit_sets = glv ? 2 : 1;
     const unsigned units = (fold ? 1 : (glv ? Wh : W));
-    auto group_first_unit = [&](unsigned g) { return (unsigned)(((uint64_t)units * g) / ngroups); };   // balanced split
+    // B200ZK_MSM_GROUP_UNITS = "u1,u2,...": explicit group sizes in windows (top windows first), e.g. "7,1": the tail of the seven
+    // top windows runs under the bucket kernel of the last one.  Ignored unless the sizes add up to the number of windows.
+    unsigned bounds[17] = {0};
+    bool custom_units = false;
+    if (!fold && nparts == 1) {
+        static const char* gu_env = getenv("B200ZK_MSM_GROUP_UNITS");
+        if (gu_env) {
+            unsigned k = 0, sum = 0;
+            const char* w = gu_env;
+            while (*w && k < 16) {
+                unsigned v = (unsigned)strtoul(w, const_cast<char**>(&w), 10);
+                if (v) { sum += v; bounds[++k] = sum; }
+                while (*w == ',' || *w == ' ') ++w;
+            }
+            if (k >= 1 && sum == units) { custom_units = true; ngroups = k; }
+        }
+    }
+    auto group_first_unit = [&](unsigned g) {
+        return custom_units ? bounds[g] : (unsigned)(((uint64_t)units * g) / ngroups);                  // default: balanced split
+    };
     const uint32_t rmw = nparts > 1 ? 1u : 0u;               // bucket kernels add into the shared buckets
 
     // Streams.  One group and one part (every MSM of a proof, the 2^20 benchmark point): nothing to overlap inside the MSM, so
