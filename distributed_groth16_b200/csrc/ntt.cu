@@ -299,7 +299,13 @@ static int get_plan(b200zk_ctx* ctx, cudaStream_t st, unsigned log_n, bool inver
     NttPlan* pl = new NttPlan();
     pl->log_n = log_n; pl->inverse = inverse;
     pl->coset.lo = nullptr; pl->shift.lo = nullptr;
-    pl->npass = log_n == 0 ? 0 : (log_n + MAX_LOG_R - 1) / MAX_LOG_R;
+    // B200ZK_NTT_MAX_LOG_R (8..11, experiment): larger tiles = fewer passes (2^22 as 11 + 11), at one or two blocks per SM
+    static const unsigned max_log_r = [] {
+        const char* e = getenv("B200ZK_NTT_MAX_LOG_R");
+        unsigned v = e ? (unsigned)atoi(e) : MAX_LOG_R;
+        return v < MAX_LOG_R ? MAX_LOG_R : (v > 11 ? 11u : v);
+    }();
+    pl->npass = log_n == 0 ? 0 : (log_n + max_log_r - 1) / max_log_r;
     for (unsigned i = 0; i < pl->npass; ++i) {
         pl->logR[i] = log_n / pl->npass + (i < log_n % pl->npass ? 1 : 0);
     }
@@ -445,9 +451,21 @@ static int ntt_run(b200zk_ctx* ctx, Slot& sl, NttPlan* pl, const Fr* d_in, Fr* d
         // threads = tile / tdiv: tdiv / 4 radix-4 units per thread per stage pair.  Measured after the stage pairing (round 2):
         // 2^20 0.257 / 0.284 ms, 2^22 0.997 / 0.996 ms, 2^24 4.28 / 4.07 ms for tdiv = 4 / 8 -> 8 from 2^23 up
         static const unsigned tdiv_env = getenv("B200ZK_NTT_TDIV") ? (unsigned)atoi(getenv("B200ZK_NTT_TDIV")) : 0;
-        const unsigned tdiv = tdiv_env ? tdiv_env : (pl->log_n >= 23 ? 8u : 4u);
+        unsigned tdiv = tdiv_env ? tdiv_env : (pl->log_n >= 23 ? 8u : 4u);
+        if (p.logR > MAX_LOG_R) {                              // big-tile experiment: fewer columns per tile, at most 512 threads
+            static const unsigned big_log_g = getenv("B200ZK_NTT_BIG_LOG_G") ? (unsigned)atoi(getenv("B200ZK_NTT_BIG_LOG_G")) : 1u;
+            if (p.logG > big_log_g) p.logG = big_log_g;
+            RG = 1u << (p.logR + p.logG);
+            while (RG / tdiv > 512) tdiv *= 2;
+            static const bool optin = [] {
+                cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+                return true;
+            }();
+            (void)optin;
+        }
         uint32_t threads = RG / tdiv < 32 ? 32 : RG / tdiv;
         size_t smem = (size_t)(2 * RG + (1u << p.logR)) * sizeof(uint4);
+        if (smem > 227 * 1024) return set_error(ctx, B200ZK_ERR_ARG, "NTT tile does not fit shared memory (B200ZK_NTT_MAX_LOG_R / B200ZK_NTT_BIG_LOG_G)");
         dim3 grid((unsigned)(((size_t)1 << log_cols) >> p.logG), batch);
         if (last && p2p && p.logM == 0 && batch >= (1u << LOG_G) && batch % (1u << LOG_G) == 0) {
             p.batch_tile = 1;
