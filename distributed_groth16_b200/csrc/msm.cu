@@ -648,13 +648,20 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
     const uint32_t B = 1u << (c - 1);
     const uint32_t nb = WB * B;
     uint32_t seg_len = B < 16 ? B : 16;
+    // Small bucket sets (<= 8192 16-bucket segments in all: a 30 k-point MSM, the small windows of a 2^16 one) are reduced by one
+    // QUAD per segment (k_msm_reduce_segments_quad) and, being pure latency chains, in 8-bucket segments whatever the caller's
+    // hint: 16 + ~16 dependent point operations per segment instead of 64 + ~15 with the 32-bucket segments a 2^20 proof prefers.
+    static const bool quad_env = !(getenv("B200ZK_MSM_QUAD_REDUCE") && getenv("B200ZK_MSM_QUAD_REDUCE")[0] == '0');
+    const bool quad_reduce = quad_env && (uint64_t)WB * (B / seg_len) <= 8192;
     {
         static const int seg_env = getenv("B200ZK_MSM_SEG") ? atoi(getenv("B200ZK_MSM_SEG")) : 0;
         if (seg_env >= 2 && (seg_env & (seg_env - 1)) == 0 && (uint32_t)seg_env <= B) seg_len = (uint32_t)seg_env;
+        else if (quad_reduce) seg_len = B < 8 ? B : 8;
         else if (ctx->msm_seg_hint && ctx->msm_seg_hint <= B) seg_len = ctx->msm_seg_hint;
     }
     const uint32_t nseg = B / seg_len;
-    const uint32_t wsplit = (fold && nseg >= 16 * 256) ? 16 : 1;
+    // fold (one bucket set): the segment partials are summed by `wsplit` blocks whose results the Horner kernel adds up
+    const uint32_t wsplit = fold ? (nseg >= 16 * 256 ? 16 : (nseg >= 1024 ? 4 : 1)) : 1;
 
     // window groups: consecutive bucket sets (GLV: whole windows, i.e. both halves).  Measured (profiles/r2_msm_groups.md):
     // at 2^20 the extra launches, the drain bubble at the end of every bucket kernel and the slowdown of the latency-bound
@@ -955,8 +962,7 @@ static int msm_dev_impl(b200zk_ctx* ctx, const MsmStreams& ms, DevBuf& ws_buf, c
         }
         {
             LaunchScope ls(ctx, st, "msm_reduce");
-            static const bool quad_env = !(getenv("B200ZK_MSM_QUAD_REDUCE") && getenv("B200ZK_MSM_QUAD_REDUCE")[0] == '0');
-            if (quad_env && (uint64_t)G.nsets * nseg <= 8192)      // latency-bound: fewer segments than the machine has warps
+            if (quad_reduce)                                       // latency-bound: fewer segments than the machine has warps
                 k_msm_reduce_segments_quad<F><<<(G.nsets * nseg * 4 + 127) / 128, 128, 0, st>>>(buckets + G.b0, G.nsets, B, seg_len,
                                                                                                partials + (size_t)G.set0 * nseg);
             else
