@@ -1,4 +1,5 @@
-// glv.cuh -- Gallant-Lambert-Vanstone scalar split for BN254 G1.
+// glv.cuh -- Gallant-Lambert-Vanstone scalar split for BN254 G1 (and, with beta^2 in place of beta, for G2 on the twist:
+// the same lambda acts there as (x, y) -> (beta^2 x, y); tools/gen_constants.py checks both).
 //
 // phi(x, y) = (beta x, y) acts on G1 as multiplication by lambda (lambda^2 + lambda + 1 = 0 mod r), so
 //   k P = k1 P + k2 phi(P),  k = k1 + k2 lambda (mod r),  |k1|, |k2| < 2^127.
